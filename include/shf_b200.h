@@ -1,0 +1,124 @@
+/* shf_b200 -- C ABI of the B200-native smallhardface inference hot path (libshf_b200.so).
+ *
+ * Every entry point takes plain pointers and sizes.  Device pointers are marked [dev]; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  All functions except `_nms` return 0 on
+ * success, a negative code otherwise, with a human-readable message from shf_last_error().
+ * Launches are asynchronous on `stream`; nothing synchronises unless stated.
+ *
+ * Activation format "h2": NHWC split-fp16, two planes [2][N][H][W][C] of __half with x = hi + lo
+ * (hi = rn(x), lo = rn(x - hi)); C must be a multiple of 8 (16-byte rows for TMA).
+ * Each declaration cites the reference interface it stands in for (paths under the reference repo).
+ */
+#ifndef SHF_B200_H
+#define SHF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* shf_last_error(void);
+int shf_abi_version(void);
+int shf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, long long* total_mem);
+
+/* ---- Net layers (caffe/src/caffe/layers/*) -------------------------------------------------- */
+
+/* ConvolutionLayer<float>::Forward (conv_layer.cpp:30-46 -> base_conv_layer.cpp:255-279) followed by the
+ * in-place ReLULayer (relu_layer.cpp:9-19), for 3x3 (pad == dilation, stride 1) and 1x1 convolutions with
+ * Cin, Cout multiples of 64.  tcgen05 implicit GEMM.  w_h2 [dev]: weights pre-packed as
+ * [2 planes][taps][Cout][Cin] fp16 of (w * 2^k); out_scale = 2^-k.  The result lands in channels
+ * [out_channel_offset, +cout) of an h2 tensor with out_channels_total channels (ConcatLayer by construction,
+ * concat_layer.cpp:47-74). */
+int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
+                   int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
+                   float out_scale, int relu, void* stream);
+
+/* conv1_1: fp32 NCHW (N,3,H,W) [dev] -> h2 (N,H,W,64); weights OIHW fp32 [dev] (64,3,3,3), pad 1. */
+int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch, int H, int W,
+                 int cout, int relu, void* stream);
+
+/* PoolingLayer MAX 2x2 stride 2 (pooling_layer.cpp:79-123,140-187), ceil-mode output (H+1)/2 x (W+1)/2. */
+int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, void* stream);
+
+/* DeconvolutionLayer with group == channels (deconv_layer.cpp:8-46; the net's conv5_256_up k4 s2 p1).
+ * w [dev]: fp32 (C,1,k,k). Output size stride*(H-1)+k-2*pad, written at a channel offset like shf_conv_igemm. */
+int shf_deconv_depthwise(const void* in_h2, const float* w, void* out_h2, int batch, int H, int W, int C, int ksize,
+                         int stride, int pad, int out_channels_total, int out_channel_offset, void* stream);
+
+/* Blob boundary (caffe/python/caffe/_caffe.cpp:205-242 exposes blobs as fp32 NCHW arrays). */
+int shf_h2_to_nchw(const void* in_h2, float* out_nchw, int batch, int H, int W, int channels_total, int channel_offset,
+                   int channels, void* stream);
+int shf_nchw_to_h2(const float* in_nchw, void* out_h2, int batch, int channels, int H, int W, int channels_total,
+                   int channel_offset, void* stream);
+
+/* ---- pre-processing (lib/utils/test_utils.py:29-46, lib/utils/blob.py:16-32, lib/test.py:30-38,147-155) -- */
+/* uint8 HWC BGR image [dev] -> one pyramid level: mean-subtract, bilinear resize by `scale` (cv2 fx=fy
+ * semantics, output out_h x out_w = rint(h*scale) x rint(w*scale)), optional mirror, zero pad to
+ * padded_h x padded_w, fp32 CHW [dev].  means: 3 host doubles (cfg.PIXEL_MEANS). */
+int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float* out_chw, int out_h, int out_w, int padded_h,
+                         int padded_w, double scale, int flip, const double* means, void* stream);
+
+/* ---- detection tail -------------------------------------------------------------------------- */
+/* cls_score*/bbox_pred* 1x1 convs + Concat/Reshape + SoftmaxLayer (softmax_layer.cpp:27-60) + the decode half of
+ * ProposalLayer.forward (lib/layers/proposal_layer.py:96-173, lib/utils/bbox_transform.py:33-93).
+ * feat_h2: host array of num_anchors [dev] pointers (head feature map per anchor, (1,H,W,C) h2).
+ * w_cls [A][2][C], b_cls [A][2], w_box [A][4][C], b_box [A][4], all fp32 [dev]; base_anchors: host [A][4].
+ * Outputs [dev]: prob (2A,H,W) fp32 = cls_prob_reshape_output; delta (4A,H,W) = bbox_pred_output;
+ * boxes (H*W*A,4) decoded+clipped, rows ordered (h,w,a); keys (H*W*A) u64 sort keys
+ * ((~score_bits)<<32 | row, ~0 for rows below score_thresh / min_size); count = rows >= score_thresh;
+ * best_key = smallest key over rows passing min_size. */
+int shf_head_decode(const void* const* feat_h2, int num_anchors, const float* w_cls, const float* b_cls,
+                    const float* w_box, const float* b_box, const float* base_anchors, int H, int W, int C,
+                    int feat_stride, float im_h, float im_w, float min_size, float score_thresh, float* prob,
+                    float* delta, float* boxes, unsigned long long* keys, int* count, unsigned long long* best_key,
+                    void* stream);
+
+/* `max_score.argsort()[::-1]` (proposal_layer.py:181) as an ascending radix sort of the keys above
+ * (ties: lower row first). */
+long long shf_sort_keys_workspace(int n);
+int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int n, void* workspace,
+                  long long workspace_bytes, void* stream);
+
+/* proposal_layer.py:183-220: R = min(count, topn) rows (1 if nothing cleared the threshold) ->
+ * out_boxes (topn,5) [0,x1,y1,x2,y2], out_probs (topn,2) [bg,fg], *out_rows = R  [all dev].
+ * If dets != NULL also performs lib/test.py:52-66,163-167 for this pass: un-mirror when flip
+ * (x1' = level_w - x2), divide by im_scale, keep fg > det_thresh, append to dets (det_cap,5) at
+ * pass_offsets[pass] and write pass_offsets[pass+1]. */
+int shf_proposal_gather(const unsigned long long* sorted_keys, const int* count, const unsigned long long* best_key,
+                        const float* prob, const float* boxes, int num_anchors, int hw, int topn, float* out_boxes,
+                        float* out_probs, int* out_rows, float* dets, int* pass_offsets, int pass, int det_cap,
+                        int flip, float level_w, float im_scale, float det_thresh, void* stream);
+
+/* Batched per-image post-processing over dets (rows [seg_begin[i], seg_end[i]) per image, all [dev]):
+ *   method 0: greedy NMS -> out_idx[i][out_cap] kept row indices relative to seg_begin[i], descending score
+ *             (lib/nms/cpu_nms.pyx:17-68 for mode 0 `(double)ovr >= thresh`; lib/nms/nms_kernel.cu:45-155 for
+ *              mode 1 `ovr > (float)thresh`; mode 2 `ovr >= (float)thresh`)
+ *   method 1: bbox_vote (lib/test.py:181-217) -> out_dets[i][out_cap][5], singleton clusters dropped.
+ * out_count[i] = rows produced.  cap_per_image bounds rows considered per image. */
+long long shf_postprocess_workspace(int num_images, int cap_per_image);
+int shf_postprocess(const float* dets, const int* seg_begin, const int* seg_end, int num_images, int cap_per_image,
+                    double thresh, int method, int mode, int* out_idx, float* out_dets, int* out_count, int out_cap,
+                    void* workspace, long long workspace_bytes, void* stream);
+
+/* lib/nms/gpu_nms.hpp:1-2 -- the reference's own symbol: HOST pointers, boxes pre-sorted by descending score,
+ * keep_out caller-allocated (boxes_num ints), synchronous, selects device_id.  `IoU > thresh` (nms_kernel.cu:82).
+ * On a CUDA error *num_out = -1 (the reference prints and continues). */
+void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim, float nms_overlap_thresh,
+          int device_id);
+int shf_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim, double thresh,
+                 int mode, int device_id);
+
+/* lib/utils/bbox.pyx: kind 0 bbox_overlaps (:14-54), 1 bbox_overlaps_IoA (:56-102), 2 bbox_overlaps_itself
+ * (:106-142).  boxes (n,4), query (k,4), out (n,k): float64 [dev]. */
+int shf_bbox_overlaps(const double* boxes, const double* query, int n, int k, int kind, double* out, void* stream);
+
+/* Validation only (not on the product path): direct fp32 convolution on h2 tensors, OIHW fp32 weights. */
+int shf_debug_conv_direct(const void* in_h2, const float* w_oihw, const float* bias, void* out_h2, int batch, int H,
+                          int W, int cin, int cout, int ksize, int dilation, int pad, int out_channels_total,
+                          int out_channel_offset, int relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHF_B200_H */

@@ -1,0 +1,391 @@
+// HBM-bound layers of the deploy nets as plain SIMT kernels (sm_100a): the 3-channel first conv,
+// 2x2 max pooling, the depthwise 2x bilinear deconvolution, layout/precision converters, the image
+// pyramid pre-processing, and a slow direct convolution used only to validate the tcgen05 kernel.
+// Activations are NHWC split-fp16 ("h2": planes [2][N][H][W][C], x = hi + lo), see common.cuh.
+#include "common.cuh"
+
+namespace {
+
+SHF_DEVICE void unpack8(const uint4& v, __half (&h)[8]) {
+  const __half2* p = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[2 * i] = __low2half(p[i]);
+    h[2 * i + 1] = __high2half(p[i]);
+  }
+}
+SHF_DEVICE uint4 pack8(const __half (&h)[8]) {
+  uint4 v;
+  __half2* p = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __halves2half2(h[2 * i], h[2 * i + 1]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv1_1: fp32 NCHW (N,3,H,W) -> h2 NHWC (N,H,W,64), 3x3 pad 1, + bias + ReLU.
+// Replaces base_conv_layer.cpp:255-279 for the K=27 first layer (HBM-bound: AI 12.9 FLOP/B,
+// SURVEY 8d) -- not worth a tensor-core tile; one thread per output pixel, 64 fp32 accumulators,
+// weights broadcast from shared memory, 128-byte coalesced stores per plane.
+// ---------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, __half* __restrict__ out,
+                                                         int N, int H, int W, int relu) {
+  __shared__ float ws[27][COUT];     // [c*9 + r*3 + s][o]
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    const int o = i / 27, k = i % 27;            // weights arrive OIHW: w[o][c][r][s]
+    ws[k][o] = w[i];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long npix = (long long)N * H * W;
+  const size_t plane = (size_t)npix * COUT;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float v[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iy = y + r - 1, ix = x + s - 1;
+          v[c * 9 + r * 3 + s] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                                     ? __ldg(in + (((size_t)n * 3 + c) * H + iy) * W + ix) : 0.f;
+        }
+    __half* ohi = out + (size_t)pix * COUT;
+    __half* olo = ohi + plane;
+#pragma unroll 1
+    for (int o0 = 0; o0 < COUT; o0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 27; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[k], ws[k][o0 + j], acc[j]);
+      __half hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = acc[j] + bs[o0 + j];
+        if (relu) t = fmaxf(t, 0.f);
+        split_h2(t, hi[j], lo[j]);
+      }
+      *reinterpret_cast<uint4*>(ohi + o0) = pack8(hi);
+      *reinterpret_cast<uint4*>(olo + o0) = pack8(lo);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2x2 / stride-2 max pooling on h2 NHWC (pooling_layer.cpp:140-187; windows clipped to the image,
+// ceil-mode output size).  One thread = one output pixel x 8 channels (16-byte vectors per plane).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2x2_h2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                                            int N, int H, int W, int C, int HO, int WO) {
+  const int cv = C / 8;
+  const long long total = (long long)N * HO * WO * cv;
+  const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int ox = (int)((i / cv) % WO);
+    const int oy = (int)((i / ((long long)cv * WO)) % HO);
+    const int n = (int)(i / ((long long)cv * WO * HO));
+    float best[8];
+    __half bh[8], bl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -3.402823466e38f; bh[j] = __float2half(0.f); bl[j] = __float2half(0.f); }
+    for (int dy = 0; dy < 2; ++dy) {
+      const int iy = oy * 2 + dy;
+      if (iy >= H) continue;
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ix = ox * 2 + dx;
+        if (ix >= W) continue;
+        const size_t off = (((size_t)n * H + iy) * W + ix) * C + (size_t)c8 * 8;
+        const uint4 vh = __ldg(reinterpret_cast<const uint4*>(in + off));
+        const uint4 vl = __ldg(reinterpret_cast<const uint4*>(in + in_plane + off));
+        __half h[8], l[8];
+        unpack8(vh, h);
+        unpack8(vl, l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = join_h2(h[j], l[j]);
+          if (v > best[j]) { best[j] = v; bh[j] = h[j]; bl[j] = l[j]; }      // first maximum wins, strict >
+        }
+      }
+    }
+    const size_t o = (((size_t)n * HO + oy) * WO + ox) * C + (size_t)c8 * 8;
+    *reinterpret_cast<uint4*>(out + o) = pack8(bh);
+    *reinterpret_cast<uint4*>(out + out_plane + o) = pack8(bl);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Depthwise transposed convolution (group == C, one filter per channel), e.g. conv5_256_up: k4 s2 p1.
+// Replaces deconv_layer.cpp:30-46 -> base_conv_layer.cpp:281-297 (256 K=1 GEMMs) + col2im
+// (im2col.cpp:163-197).  Writes into channels [c_off, c_off+C) of a wider NHWC tensor (the concat).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
+                                                           __half* __restrict__ out, int N, int H, int W, int C,
+                                                           int K, int S, int P, int HO, int WO, int CT, int c_off) {
+  const int cv = C / 8;
+  const long long total = (long long)N * HO * WO * cv;
+  const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * CT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int ox = (int)((i / cv) % WO);
+    const int oy = (int)((i / ((long long)cv * WO)) % HO);
+    const int n = (int)(i / ((long long)cv * WO * HO));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < K; ++ky) {                 // same (ky, kx) accumulation order as col2im
+      const int ty = oy + P - ky;
+      if (ty < 0 || ty % S) continue;
+      const int iy = ty / S;
+      if (iy >= H) continue;
+      for (int kx = 0; kx < K; ++kx) {
+        const int tx = ox + P - kx;
+        if (tx < 0 || tx % S) continue;
+        const int ix = tx / S;
+        if (ix >= W) continue;
+        const size_t off = (((size_t)n * H + iy) * W + ix) * C + (size_t)c8 * 8;
+        __half h[8], l[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(in + off)), h);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(in + in_plane + off)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          acc[j] += join_h2(h[j], l[j]) * __ldg(w + ((size_t)(c8 * 8 + j) * K + ky) * K + kx);
+      }
+    }
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_h2(acc[j], hi[j], lo[j]);
+    const size_t o = (((size_t)n * HO + oy) * WO + ox) * CT + c_off + (size_t)c8 * 8;
+    *reinterpret_cast<uint4*>(out + o) = pack8(hi);
+    *reinterpret_cast<uint4*>(out + out_plane + o) = pack8(lo);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Layout / precision converters (the Blob.data boundary: Caffe blobs are fp32 NCHW)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) h2_to_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int N,
+                                                         int H, int W, int CT, int c_off, int C) {
+  // one thread per (n, y, x, c): reads are channel-contiguous; a 32x32 smem transpose would make both
+  // sides coalesced, but this only runs when a host reads an intermediate blob (debug / parity tests)
+  const long long total = (long long)N * H * W * C;
+  const size_t plane = (size_t)N * H * W * CT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    const size_t src = (size_t)pix * CT + c_off + c;
+    out[(((size_t)n * C + c) * H + y) * W + x] = join_h2(in[src], in[plane + src]);
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_h2_kernel(const float* __restrict__ in, __half* __restrict__ out, int N,
+                                                         int C, int H, int W, int CT, int c_off) {
+  const long long total = (long long)N * H * W * C;
+  const size_t plane = (size_t)N * H * W * CT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    __half hi, lo;
+    split_h2(in[(((size_t)n * C + c) * H + y) * W + x], hi, lo);
+    const size_t dst = (size_t)pix * CT + c_off + c;
+    out[dst] = hi;
+    out[plane + dst] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pyramid level pre-processing: uint8 HWC BGR image -> mean-subtracted, bilinearly resized, optionally
+// mirrored, zero-padded fp32 NCHW level blob.  Fuses lib/utils/test_utils.py:29-46 (mean subtract, then
+// cv2.resize(fx, fy, INTER_LINEAR) on the float64 image), blob.py:16-32 (HWC->NCHW, float32),
+// lib/test.py:147-155 (flip = mirror of the UNPADDED blob) and lib/test.py:30-38 (pad to x16).
+// Arithmetic follows oracle/preprocess.py:resize_linear: double coefficients, lerp S0+(S1-S0)*a with
+// fused multiply-add, horizontal then vertical (what opencv 4.13 computes for CV_64F).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_level_kernel(const uint8_t* __restrict__ img, int h, int w,
+                                                               float* __restrict__ out, int oh, int ow, int HP, int WP,
+                                                               double inv_scale, int identity, int flip, double m0,
+                                                               double m1, double m2) {
+  const long long total = (long long)HP * WP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % WP), y = (int)(i / WP);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (x < ow && y < oh) {
+      const int xs = flip ? (ow - 1 - x) : x;           // mirror the unpadded level
+      const double mean[3] = {m0, m1, m2};
+      double res[3];
+      if (identity) {
+        const uint8_t* px = img + ((size_t)y * w + xs) * 3;
+        for (int c = 0; c < 3; ++c) res[c] = (double)(float)px[c] - mean[c];
+      } else {
+        double fx = __dadd_rn(__dmul_rn((double)xs + 0.5, inv_scale), -0.5);
+        double fy = __dadd_rn(__dmul_rn((double)y + 0.5, inv_scale), -0.5);
+        int sx = (int)floor(fx), sy = (int)floor(fy);
+        double ax = fx - (double)sx, ay = fy - (double)sy;
+        if (sx < 0) { sx = 0; ax = 0.0; }
+        if (sx >= w - 1) { sx = w - 1; ax = 0.0; }
+        if (sy < 0) { sy = 0; ay = 0.0; }
+        if (sy >= h - 1) { sy = h - 1; ay = 0.0; }
+        const int sx1 = min(sx + 1, w - 1), sy1 = min(sy + 1, h - 1);
+        const uint8_t* p00 = img + ((size_t)sy * w + sx) * 3;
+        const uint8_t* p01 = img + ((size_t)sy * w + sx1) * 3;
+        const uint8_t* p10 = img + ((size_t)sy1 * w + sx) * 3;
+        const uint8_t* p11 = img + ((size_t)sy1 * w + sx1) * 3;
+        for (int c = 0; c < 3; ++c) {
+          const double a = (double)(float)p00[c] - mean[c], b = (double)(float)p01[c] - mean[c];
+          const double d = (double)(float)p10[c] - mean[c], e = (double)(float)p11[c] - mean[c];
+          const double t0 = fma(b - a, ax, a);
+          const double t1 = fma(e - d, ax, d);
+          res[c] = fma(t1 - t0, ay, t0);
+        }
+      }
+      r0 = (float)res[0]; r1 = (float)res[1]; r2 = (float)res[2];
+    }
+    out[(size_t)0 * HP * WP + i] = r0;
+    out[(size_t)1 * HP * WP + i] = r1;
+    out[(size_t)2 * HP * WP + i] = r2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Validation-only direct convolution on h2 NHWC (fp32 FMA, one thread per output element).
+// NOT on the product path: tests use it to check the tcgen05 kernel at sizes the CPU oracle is slow at.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_direct_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, __half* __restrict__ out,
+                                                             int N, int H, int W, int CI, int CO, int K, int dil,
+                                                             int pad, int CT, int c_off, int relu) {
+  const long long total = (long long)N * H * W * CO;
+  const size_t in_plane = (size_t)N * H * W * CI, out_plane = (size_t)N * H * W * CT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % CO);
+    const long long pix = i / CO;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float acc = 0.f;
+    for (int r = 0; r < K; ++r) {
+      const int iy = y - pad + r * dil;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < K; ++s) {
+        const int ix = x - pad + s * dil;
+        if (ix < 0 || ix >= W) continue;
+        const __half* ph = in + (((size_t)n * H + iy) * W + ix) * CI;
+        const float* pw = w + ((size_t)o * CI * K + r) * K + s;          // OIHW
+        for (int c = 0; c < CI; ++c) acc = fmaf(join_h2(ph[c], ph[in_plane + c]), pw[(size_t)c * K * K], acc);
+      }
+    }
+    acc += bias ? bias[o] : 0.f;
+    if (relu) acc = fmaxf(acc, 0.f);
+    __half hi, lo;
+    split_h2(acc, hi, lo);
+    const size_t dst = (size_t)pix * CT + c_off + o;
+    out[dst] = hi;
+    out[out_plane + dst] = lo;
+  }
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 32;            // 148 SMs x resident CTAs; grid-stride loops cover the rest
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch,
+                            int H, int W, int cout, int relu, void* stream) {
+  SHF_REQUIRE(cout == 64, "shf_conv1_c3: Cout=%d (the deploy nets' conv1_1 has 64)", cout);
+  const long long npix = (long long)batch * H * W;
+  conv3x3_c3_kernel<64><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(in_nchw, w_oihw, bias, (__half*)out_h2,
+                                                                               batch, H, W, relu);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, void* stream) {
+  SHF_REQUIRE(C % 8 == 0, "shf_maxpool2x2: C=%d must be a multiple of 8", C);
+  const int HO = (H + 1) / 2, WO = (W + 1) / 2;       // ceil mode, pooling_layer.cpp:91-94 with k=s=2, pad 0
+  const long long total = (long long)batch * HO * WO * (C / 8);
+  maxpool2x2_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)in_h2, (__half*)out_h2,
+                                                                             batch, H, W, C, HO, WO);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_deconv_depthwise(const void* in_h2, const float* w, void* out_h2, int batch, int H, int W, int C,
+                                    int ksize, int stride, int pad, int out_channels_total, int out_channel_offset,
+                                    void* stream) {
+  SHF_REQUIRE(C % 8 == 0 && out_channel_offset % 8 == 0 && out_channels_total % 8 == 0,
+              "shf_deconv_depthwise: channel counts must be multiples of 8");
+  const int HO = stride * (H - 1) + ksize - 2 * pad, WO = stride * (W - 1) + ksize - 2 * pad;   // deconv_layer.cpp:8-28
+  const long long total = (long long)batch * HO * WO * (C / 8);
+  deconv_dw_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, ksize, stride, pad, HO, WO, out_channels_total,
+      out_channel_offset);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_h2_to_nchw(const void* in_h2, float* out_nchw, int batch, int H, int W, int channels_total,
+                              int channel_offset, int channels, void* stream) {
+  const long long total = (long long)batch * H * W * channels;
+  h2_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)in_h2, out_nchw, batch, H, W,
+                                                                          channels_total, channel_offset, channels);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_nchw_to_h2(const float* in_nchw, void* out_h2, int batch, int channels, int H, int W,
+                              int channels_total, int channel_offset, void* stream) {
+  const long long total = (long long)batch * H * W * channels;
+  nchw_to_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in_nchw, (__half*)out_h2, batch, channels, H,
+                                                                          W, channels_total, channel_offset);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float* out_chw, int out_h, int out_w,
+                                    int padded_h, int padded_w, double scale, int flip, const double* means,
+                                    void* stream) {
+  SHF_REQUIRE(out_h <= padded_h && out_w <= padded_w && h > 0 && w > 0, "shf_preprocess_level: bad geometry");
+  const long long total = (long long)padded_h * padded_w;
+  preprocess_level_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      img_hwc, h, w, out_chw, out_h, out_w, padded_h, padded_w, 1.0 / scale, scale == 1.0 ? 1 : 0, flip, means[0],
+      means[1], means[2]);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_debug_conv_direct(const void* in_h2, const float* w_oihw, const float* bias, void* out_h2, int batch,
+                                     int H, int W, int cin, int cout, int ksize, int dilation, int pad,
+                                     int out_channels_total, int out_channel_offset, int relu, void* stream) {
+  const long long total = (long long)batch * H * W * cout;
+  conv_direct_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)in_h2, w_oihw, bias, (__half*)out_h2, batch, H, W, cin, cout, ksize, dilation, pad,
+      out_channels_total, out_channel_offset, relu);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}

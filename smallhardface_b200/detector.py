@@ -1,0 +1,172 @@
+"""Image-pyramid detection driver on one GPU: the device-resident equivalent of ``lib/test.py:109-178``
+(``detect``) + ``lib/test.py:21-106`` (``forward_net``).
+
+Per image: one uint8 upload; then for each pyramid scale and (optionally) its mirror the level blob is
+produced on the device (``shf_preprocess_level``), the net runs, and the pass's detections (un-mirrored,
+unscaled, score > 0.05) are appended to a device-side list; finally box voting or NMS runs batched over
+all images of the call.  Only the final boxes leave the GPU -- the reference copies a float32 blob per
+level to the device, both head blobs back (``proposal_layer.py:96-98``), and runs decode, sort and the
+O(n * clusters) ``bbox_vote`` loop in NumPy under the GIL.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import caffe_proto as cp
+from . import lib as L
+from .engine import GpuNet, _ptr, _stream
+from .graph import NetSpec, TEST, load_weights
+
+
+@dataclass
+class DetectConfig:
+    """The ``cfg.TEST.*`` / ``cfg.*`` keys the hot path reads (``configs/default.toml``)."""
+    scales: Sequence[int] = (100, 300, 600, 1000, 1400)        # TEST.SCALES
+    pyramid_base_size: Sequence[int] = (800, 1200)             # TEST.PYRAMID_BASE_SIZE
+    max_size: int = 2000                                       # TEST.MAX_SIZE (single-scale mode)
+    flip: bool = True                                          # TEST.FLIP
+    nms_method: str = "BBOX_VOTE"                              # TEST.NMS_METHOD
+    nms_thresh: float = 0.4                                    # TEST.NMS_THRESH
+    thresh: float = 0.05                                       # test_net(thresh=0.05)
+    n_dets_per_module: int = 10000                             # TEST.N_DETS_PER_MODULE
+    score_thresh: float = 0.002                                # TEST.SCORE_THRESH
+    anchor_min_size: float = 0.0                               # TEST.ANCHOR_MIN_SIZE
+    max_resolution: int = 16                                   # MAX_RESOLUTION
+    pixel_means: Sequence[float] = (102.9801, 115.9465, 122.7717)   # PIXEL_MEANS
+    nms_mode: int = 0                                          # 0 = cpu_nms (>=), 1 = gpu_nms (>)
+    max_dets_out: int = 4096                                   # rows returned per image (post vote / NMS)
+
+
+def compute_scaling_factor(im_shape, target_size, max_size):
+    """``lib/utils/test_utils.py:8-26`` (host scalar logic)."""
+    lo, hi = min(im_shape[0], im_shape[1]), max(im_shape[0], im_shape[1])
+    s = float(target_size) / float(lo)
+    if np.round(s * hi) > max_size:
+        s = float(max_size) / float(hi)
+    return s
+
+
+def pyramid_scales(im_shape, cfg: DetectConfig):
+    """``lib/test.py:131-137``; single-scale mode ``lib/test.py:119-122`` when one scale is configured."""
+    if len(cfg.scales) > 1:
+        base = compute_scaling_factor(im_shape, cfg.pyramid_base_size[0], cfg.pyramid_base_size[1])
+        return [float(s) / cfg.pyramid_base_size[0] * base for s in cfg.scales]
+    return [compute_scaling_factor(im_shape, cfg.scales[0], cfg.max_size)]
+
+
+def level_geometry(h, w, s, mult=16):
+    """Resized size (cv2: rint(src * f), half to even) and the x16-padded size (``lib/test.py:34-36``)."""
+    oh = h if s == 1.0 else int(np.rint(h * s))
+    ow = w if s == 1.0 else int(np.rint(w * s))
+    return oh, ow, -(-oh // mult) * mult, -(-ow // mult) * mult
+
+
+class Detector:
+    def __init__(self, prototxt, caffemodel, device="cuda:0", cfg: DetectConfig | None = None):
+        self.cfg = cfg or DetectConfig()
+        self.device = torch.device(device)
+        net_param = cp.read_net_text(prototxt) if isinstance(prototxt, str) else prototxt
+        model = cp.read_net_binary(caffemodel) if isinstance(caffemodel, str) else caffemodel
+        spec = NetSpec(net_param, TEST)
+        params = load_weights(spec, model)
+        self.net = GpuNet(spec, params, device, pre_nms_topn=self.cfg.n_dets_per_module,
+                          score_thresh=self.cfg.score_thresh, min_size=self.cfg.anchor_min_size)
+        self._means = (C.c_double * 3)(*self.cfg.pixel_means)
+        self._bufs = {}
+
+    # ------------------------------------------------------------------------------------------
+    def upload(self, images: List[np.ndarray]) -> List[torch.Tensor]:
+        """uint8 HWC BGR host images -> device tensors (through pinned staging, async on the current stream)."""
+        out = []
+        for im in images:
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError("images must be uint8 HxWx3 (cv2.imread layout)")
+            pin = torch.from_numpy(np.ascontiguousarray(im)).pin_memory()
+            out.append(pin.to(self.device, non_blocking=True))
+        return out
+
+    def _buffers(self, batch: int, passes: int):
+        key = (batch, passes)
+        b = self._bufs.get(key)
+        if b is None:
+            cap = passes * self.net.cfg["pre_nms_topn"]
+            dev = self.device
+            ws_bytes = int(L.load().shf_postprocess_workspace(batch, cap))
+            b = dict(cap=cap, dets=torch.empty((batch, cap, 5), dtype=torch.float32, device=dev),
+                     offs=torch.zeros((batch, passes + 1), dtype=torch.int32, device=dev),
+                     seg_begin=(torch.arange(batch, dtype=torch.int32, device=dev) * cap).contiguous(),
+                     seg_end=torch.empty((batch,), dtype=torch.int32, device=dev),
+                     out_dets=torch.empty((batch, self.cfg.max_dets_out, 5), dtype=torch.float32, device=dev),
+                     out_idx=torch.empty((batch, self.cfg.max_dets_out), dtype=torch.int32, device=dev),
+                     out_count=torch.zeros((batch,), dtype=torch.int32, device=dev),
+                     ws=torch.empty((ws_bytes,), dtype=torch.uint8, device=dev), ws_bytes=ws_bytes)
+            self._bufs[key] = b
+        return b
+
+    def _level_blob(self, img: torch.Tensor, s: float, flip: bool):
+        h, w = img.shape[0], img.shape[1]
+        oh, ow, hp, wp = level_geometry(h, w, s, self.cfg.max_resolution)
+        data = torch.empty((1, 3, hp, wp), dtype=torch.float32, device=self.device)
+        L.call("shf_preprocess_level", _ptr(img), h, w, _ptr(data), oh, ow, hp, wp, float(s), int(flip), self._means,
+               _stream())
+        self.net.launches += 1
+        return data, (oh, ow, s)
+
+    def detect_device(self, dev_images: List[torch.Tensor]):
+        """Runs the whole pipeline for a batch of device-resident images; returns the device buffers
+        (out_dets (B,max,5), out_idx (B,max), out_count (B,), dets (B,cap,5)) without synchronising."""
+        cfg = self.cfg
+        flips = (False, True) if cfg.flip else (False,)
+        nscales = len(cfg.scales) if len(cfg.scales) > 1 else 1
+        passes = nscales * len(flips)
+        B = len(dev_images)
+        b = self._buffers(B, passes)
+        b["offs"].zero_()
+        for i, img in enumerate(dev_images):
+            scales = pyramid_scales(img.shape, cfg)
+            p = 0
+            for s in scales:
+                for fl in flips:
+                    data, info = self._level_blob(img, s, fl)
+                    self.net.forward(data, info, dets=b["dets"][i], pass_offsets=b["offs"][i], pass_idx=p,
+                                     det_cap=b["cap"], flip=fl, det_thresh=cfg.thresh)
+                    p += 1
+        torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])
+        method = 1 if cfg.nms_method == "BBOX_VOTE" else 0
+        if cfg.nms_method not in ("BBOX_VOTE", "NMS"):
+            raise NotImplementedError("Unknown NMS method: {}".format(cfg.nms_method))     # lib/test.py:173-175
+        L.call("shf_postprocess", _ptr(b["dets"]), _ptr(b["seg_begin"]), _ptr(b["seg_end"]), B, b["cap"],
+               float(cfg.nms_thresh), method, int(cfg.nms_mode), _ptr(b["out_idx"]), _ptr(b["out_dets"]),
+               _ptr(b["out_count"]), cfg.max_dets_out, _ptr(b["ws"]), b["ws_bytes"], _stream())
+        self.net.launches += 3 + B
+        return b
+
+    def download(self, b, B: int) -> List[np.ndarray]:
+        """Device results -> list of (M,5) arrays ``[x1,y1,x2,y2,score]`` (float64 for BBOX_VOTE, as
+        ``bbox_vote`` returns; float32 rows of ``dets`` for NMS)."""
+        counts = b["out_count"][:B].cpu().numpy()
+        out = []
+        if self.cfg.nms_method == "BBOX_VOTE":
+            host = b["out_dets"][:B].cpu().numpy()
+            for i in range(B):
+                out.append(host[i, :counts[i]].astype(np.float64))
+        else:
+            for i in range(B):
+                idx = b["out_idx"][i, :int(counts[i])].long()
+                out.append(b["dets"][i].index_select(0, idx).cpu().numpy())
+        return out
+
+    def detect(self, images: List[np.ndarray]) -> List[np.ndarray]:
+        dev = self.upload(images)
+        b = self.detect_device(dev)
+        return self.download(b, len(images))
+
+    def raw_detections(self, b, i: int) -> np.ndarray:
+        """Pre-vote detections of image i (concatenated passes, score > thresh), for parity checks."""
+        n = int(b["offs"][i, -1].item())
+        return b["dets"][i, :n].cpu().numpy()

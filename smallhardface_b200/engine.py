@@ -1,0 +1,416 @@
+"""GPU executor for the deploy nets: NetSpec -> a static plan of sm_100a kernel launches.
+
+What Caffe does per forward (``net.cpp:516-532``: for every layer ``Reshape`` + ``Forward_gpu``, one
+blob per top, cuDNN re-planning on each new shape) becomes a short list of fused launches over
+NHWC split-fp16 tensors:
+
+  * Convolution + in-place ReLU            -> one tcgen05 implicit-GEMM launch (``shf_conv_igemm``)
+  * conv1_1 (3 input channels)              -> ``shf_conv1_c3``
+  * Pooling MAX 2x2/2                       -> ``shf_maxpool2x2``
+  * depthwise Deconvolution                 -> ``shf_deconv_depthwise``
+  * Concat(axis=1)                          -> nothing: producers write at channel offsets of one tensor
+  * Split / Reshape                         -> aliasing
+  * cls/bbox 1x1 convs + Concat/Reshape + Softmax + Reshape + Python ProposalLayer
+                                            -> ``shf_head_decode`` + ``shf_sort_keys`` + ``shf_proposal_gather``
+
+PyTorch is used for device memory and streams only.  There is no CPU path: a layer pattern the plan
+does not recognise raises, it is never computed some other way.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .graph import NetSpec, LayerSpec, parse_python_param_str
+
+F32 = np.float32
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# split-fp16 helpers (host side; used once at load time for weights)
+# ------------------------------------------------------------------------------------------------
+def split_h2_np(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    x = np.asarray(x, dtype=np.float32)
+    hi = x.astype(np.float16)
+    lo = (x - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def pack_conv_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
+    """(Cout, Cin, kh, kw) fp32 -> ([2][taps][Cout][Cin] fp16 of w * 2^k, k).  The power-of-two
+    pre-scale keeps both the hi and the lo part of typical weights (|w| ~ 1e-2) in fp16's normal
+    range, so hi + lo carries ~22 mantissa bits; the conv epilogue multiplies by 2^-k (exact)."""
+    w = np.asarray(w_oihw, dtype=np.float32)
+    co, ci, kh, kw = w.shape
+    amax = float(np.abs(w).max())
+    k = 0 if amax == 0 or not np.isfinite(amax) else int(14 - math.ceil(math.log2(amax)))
+    k = max(-14, min(k, 24))
+    ws = w * np.float32(2.0 ** k)
+    hi, lo = split_h2_np(ws)
+    def lay(a):
+        return np.ascontiguousarray(a.transpose(2, 3, 0, 1).reshape(kh * kw, co, ci))
+    return np.stack([lay(hi), lay(lo)]), k
+
+
+class H2:
+    """NHWC split-fp16 activation tensor: torch.float16 (2, N, H, W, C), optionally a channel window
+    [c_off, c_off + C) of a wider tensor (how Concat is realised)."""
+
+    __slots__ = ("t", "c_off", "c")
+
+    def __init__(self, t: torch.Tensor, c_off: int = 0, c: Optional[int] = None):
+        self.t = t
+        self.c_off = c_off
+        self.c = t.shape[4] if c is None else c
+
+    @property
+    def n(self): return self.t.shape[1]
+    @property
+    def h(self): return self.t.shape[2]
+    @property
+    def w(self): return self.t.shape[3]
+    @property
+    def ctot(self): return self.t.shape[4]
+
+    @staticmethod
+    def empty(n, h, w, c, device):
+        return H2(torch.empty((2, n, h, w, c), dtype=torch.float16, device=device))
+
+    def to_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.t.device)
+        L.call("shf_h2_to_nchw", _ptr(self.t), _ptr(out), self.n, self.h, self.w, self.ctot, self.c_off, self.c, _stream())
+        return out
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor) -> "H2":
+        x = x.contiguous().float()
+        n, c, h, w = x.shape
+        out = H2.empty(n, h, w, c, x.device)
+        L.call("shf_nchw_to_h2", _ptr(x), _ptr(out.t), n, c, h, w, c, 0, _stream())
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# plan
+# ------------------------------------------------------------------------------------------------
+class _Op:
+    kind = ""
+
+    def __init__(self, spec: LayerSpec):
+        self.spec = spec
+
+
+class GpuNet:
+    """Executes a NetSpec on one GPU.  ``forward`` takes the padded fp32 NCHW ``data`` tensor already on
+    the device plus ``im_info`` and leaves every materialised blob in ``self.tensors``."""
+
+    def __init__(self, spec: NetSpec, params: Dict[str, np.ndarray], device="cuda:0", pre_nms_topn=10000,
+                 score_thresh=0.002, min_size=0.0):
+        L.load()
+        self.spec = spec
+        self.device = torch.device(device)
+        self.cfg = dict(pre_nms_topn=int(pre_nms_topn), score_thresh=float(score_thresh), min_size=float(min_size))
+        self.launches = 0
+        self._plan(params)
+        self.tensors: "OrderedDict[str, object]" = OrderedDict()
+
+    # -- planning --------------------------------------------------------------------------------
+    def _plan(self, params):
+        spec = self.spec
+        spec.infer_shapes({})
+        layers = spec.layers
+        producers = {}
+        consumers: Dict[str, List[LayerSpec]] = {}
+        for l in layers:
+            for t in l.tops:
+                if t not in l.bottoms or l.type == "Input":
+                    producers[t] = l
+            for b in l.bottoms:
+                consumers.setdefault(b, []).append(l)
+        self.producers, self.consumers = producers, consumers
+        fused = set()
+        self.tail = None
+        # ---- detection tail pattern ---------------------------------------------------------------
+        for l in layers:
+            if l.type == "Python":
+                if (l.p["module"], l.p["layer"]) != ("lib.layers.proposal_layer", "ProposalLayer"):
+                    raise L.ShfError("Python layer %s.%s has no CUDA implementation on this path" % (l.p["module"], l.p["layer"]))
+                self.tail = self._plan_tail(l, params, fused)
+        # ---- concat-by-offset ------------------------------------------------------------------------
+        self.concat_dst: Dict[str, Tuple[str, int, int]] = {}
+        for l in layers:
+            if l.type == "Concat" and l.name not in fused:
+                if l.p["axis"] != 1:
+                    raise L.ShfError("Concat %s: only the channel axis is supported outside the detection tail" % l.name)
+                off = 0
+                shapes = spec.infer_shapes({})
+                total = sum(shapes[b][1] for b in l.bottoms)
+                for b in l.bottoms:
+                    c = shapes[b][1]
+                    if len(consumers.get(b, [])) != 1 or producers[b].type not in ("Convolution", "Deconvolution"):
+                        raise L.ShfError("Concat %s: bottom %s must be a conv/deconv output used only here" % (l.name, b))
+                    if off % 8 or c % 8:
+                        raise L.ShfError("Concat %s: channel offsets must be multiples of 8" % l.name)
+                    self.concat_dst[b] = (l.tops[0], off, total)
+                    off += c
+        # ---- body ops ----------------------------------------------------------------------------------
+        self.ops: List[Tuple[str, LayerSpec, dict]] = []
+        self.fused_blobs = set()
+        i = 0
+        dev = self.device
+        while i < len(layers):
+            l = layers[i]
+            if l.name in fused or l.type in ("Input", "Split", "Concat"):
+                if l.type == "Split":
+                    self.ops.append(("alias", l, {}))
+                i += 1
+                continue
+            if l.type == "Convolution":
+                p = l.p
+                relu = False
+                if i + 1 < len(layers) and layers[i + 1].type == "ReLU" and layers[i + 1].bottoms == l.tops \
+                        and layers[i + 1].tops == l.tops and layers[i + 1].p["negative_slope"] == 0.0:
+                    relu = True
+                w = params[l.param_keys[0]]
+                b = params[l.param_keys[1]] if p["bias_term"] else None
+                if (p["sh"], p["sw"]) != (1, 1) or p["group"] != 1 or p["kh"] != p["kw"] or p["dh"] != p["dw"] or p["ph"] != p["pw"]:
+                    raise L.ShfError("conv %s: only stride-1, ungrouped, square kernels are on the hot path" % l.name)
+                cin = w.shape[1]
+                st = dict(relu=relu, k=p["kh"], dil=p["dh"], cout=p["num_output"], cin=cin,
+                          bias=None if b is None else torch.from_numpy(np.ascontiguousarray(b, F32)).to(dev))
+                if cin == 3:
+                    if not (p["kh"] == 3 and p["ph"] == 1 and p["dh"] == 1 and p["num_output"] == 64):
+                        raise L.ShfError("conv %s: 3-channel convs must be 3x3 pad 1 with 64 outputs" % l.name)
+                    st["w"] = torch.from_numpy(np.ascontiguousarray(w, F32)).to(dev)
+                    self.ops.append(("conv1", l, st))
+                else:
+                    if p["kh"] not in (1, 3) or (p["kh"] == 3 and p["ph"] != p["dh"]) or (p["kh"] == 1 and p["ph"] != 0):
+                        raise L.ShfError("conv %s: need 3x3 with pad == dilation or 1x1 with pad 0" % l.name)
+                    if cin % 64 or p["num_output"] % 64:
+                        raise L.ShfError("conv %s: channel counts must be multiples of 64 (got %d -> %d)" % (l.name, cin, p["num_output"]))
+                    packed, k = pack_conv_weights(w)
+                    st["w"] = torch.from_numpy(packed).to(dev)
+                    st["scale"] = float(2.0 ** (-k))
+                    self.ops.append(("conv", l, st))
+                i += 2 if relu else 1
+                continue
+            if l.type == "ReLU":
+                raise L.ShfError("ReLU %s is not fused into a preceding convolution (unsupported pattern)" % l.name)
+            if l.type == "Pooling":
+                p = l.p
+                if (p["pool"], p["kh"], p["kw"], p["sh"], p["sw"], p["ph"], p["pw"]) != (0, 2, 2, 2, 2, 0, 0):
+                    raise L.ShfError("pool %s: only MAX 2x2 stride 2 is on the hot path" % l.name)
+                self.ops.append(("pool", l, {}))
+            elif l.type == "Deconvolution":
+                p = l.p
+                w = params[l.param_keys[0]]
+                if not (p["group"] == w.shape[0] == p["num_output"] and w.shape[1] == 1 and not p["bias_term"]
+                        and p["kh"] == p["kw"] and p["sh"] == p["sw"] and p["ph"] == p["pw"] and p["dh"] == 1):
+                    raise L.ShfError("deconv %s: only depthwise, bias-free, square deconvolutions are on the hot path" % l.name)
+                self.ops.append(("deconv", l, dict(w=torch.from_numpy(np.ascontiguousarray(w, F32)).to(dev),
+                                                   k=p["kh"], s=p["sh"], pad=p["ph"])))
+            elif l.type == "Reshape":
+                raise L.ShfError("Reshape %s outside the detection tail is not supported" % l.name)
+            else:
+                raise L.ShfError("layer %s of type %s has no CUDA implementation on this path" % (l.name, l.type))
+            i += 1
+
+    def _plan_tail(self, prop: LayerSpec, params, fused) -> dict:
+        spec = self.spec
+        by_top = {}
+        for l in spec.layers:
+            for t in l.tops:
+                if t not in l.bottoms:
+                    by_top[t] = l
+        lp = parse_python_param_str(prop.p["param_str"])
+        from .anchors import generate_anchors
+        anchors = generate_anchors(base_size=lp.get("base_size", 16), ratios=lp.get("ratios", (0.5, 1, 2)),
+                                   scales=lp.get("scales", (8, 16, 32)), shifts=lp.get("shifts", [0]),
+                                   strides=lp["feat_stride"])
+        A = anchors.shape[0]
+        if lp.get("num_feats", 1) != 1 or len(prop.bottoms) != 3:
+            raise L.ShfError("ProposalLayer with refinement bottoms / num_feats != 1 is not on the test path")
+        cls_blob, box_blob, info_blob = prop.bottoms
+        chain = []
+        r2 = by_top[cls_blob]                         # Reshape (0,2A,-1,0)
+        sm = by_top[r2.bottoms[0]] if r2.type == "Reshape" else None
+        if sm is None or sm.type != "Softmax" or sm.p["axis"] != 1:
+            raise L.ShfError("detection tail: expected Reshape <- Softmax(axis 1) feeding the ProposalLayer")
+        src = by_top[sm.bottoms[0]]
+        chain += [r2, sm, src]
+        heads = []                                     # per anchor: (feature blob, wc(2,C), bc(2), wb(4,C), bb(4))
+        def conv_wb(l):
+            w = params[l.param_keys[0]]
+            if l.type != "Convolution" or w.shape[2:] != (1, 1):
+                raise L.ShfError("detection tail: %s must be a 1x1 convolution" % l.name)
+            b = params[l.param_keys[1]] if l.p["bias_term"] else np.zeros(w.shape[0], F32)
+            return w[:, :, 0, 0], b
+        box_src = by_top[box_blob]
+        if src.type == "Reshape":                     # standard template: one cls conv (2A ch), one bbox conv (4A ch)
+            cls_l = by_top[src.bottoms[0]]
+            wc, bc = conv_wb(cls_l)
+            wb, bb = conv_wb(box_src)
+            if wc.shape[0] != 2 * A or wb.shape[0] != 4 * A or cls_l.bottoms != box_src.bottoms:
+                raise L.ShfError("detection tail: cls/bbox convs do not match %d anchors" % A)
+            for a in range(A):
+                heads.append((cls_l.bottoms[0], wc[[a, A + a]], bc[[a, A + a]], wb[4 * a:4 * a + 4], bb[4 * a:4 * a + 4]))
+            chain += [cls_l, box_src]
+        elif src.type == "Concat" and src.p["axis"] == 2 and box_src.type == "Concat" and box_src.p["axis"] == 1:
+            if len(src.bottoms) != A or len(box_src.bottoms) != A:
+                raise L.ShfError("detection tail: %d cls maps for %d anchors" % (len(src.bottoms), A))
+            chain.append(box_src)
+            for a in range(A):
+                cl, bl = by_top[src.bottoms[a]], by_top[box_src.bottoms[a]]
+                wc, bc = conv_wb(cl)
+                wb, bb = conv_wb(bl)
+                if wc.shape[0] != 2 or wb.shape[0] != 4 or cl.bottoms != bl.bottoms:
+                    raise L.ShfError("detection tail: per-anchor cls/bbox convs must be 2/4 channels on one head")
+                heads.append((cl.bottoms[0], wc, bc, wb, bb))
+                chain += [cl, bl]
+        else:
+            raise L.ShfError("detection tail: unrecognised cls/bbox wiring")
+        for l in chain:
+            fused.add(l.name)
+        fused.add(prop.name)
+        dev = self.device
+        Cf = heads[0][1].shape[1]
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x, F32)).to(dev)
+        return dict(A=A, C=Cf, feats=[h[0] for h in heads], anchors=np.ascontiguousarray(anchors, F32),
+                    wc=t(np.stack([h[1] for h in heads])), bc=t(np.stack([h[2] for h in heads])),
+                    wb=t(np.stack([h[3] for h in heads])), bb=t(np.stack([h[4] for h in heads])),
+                    stride=int(lp["feat_stride"][0]), tops=prop.tops, info=info_blob,
+                    cls_blob=cls_blob, box_blob=box_blob, fused=[l.name for l in chain])
+
+    # -- execution -------------------------------------------------------------------------------------
+    def _alloc_out(self, blob: str, n, h, w, c) -> H2:
+        if blob in self.concat_dst:
+            top, off, total = self.concat_dst[blob]
+            dst = self.tensors.get(top)
+            if dst is None or (dst.n, dst.h, dst.w, dst.ctot) != (n, h, w, total):
+                dst = H2.empty(n, h, w, total, self.device)
+                self.tensors[top] = dst
+            out = H2(dst.t, off, c)
+        else:
+            out = H2.empty(n, h, w, c, self.device)
+        self.tensors[blob] = out
+        return out
+
+    def forward(self, data: torch.Tensor, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False,
+                det_thresh=0.05):
+        """data: (N,3,H,W) fp32 on the device.  im_info: (h, w, scale) of the unpadded level.
+        Returns (boxes (topn,5), probs (topn,2), rows (1,) int32) device tensors; when ``dets`` is given the
+        pass is also appended to the image-level detection list (see shf_proposal_gather)."""
+        T = self.tensors
+        T.clear()
+        T["data"] = data
+        st = _stream()
+        for kind, l, s in self.ops:
+            if kind == "alias":
+                for t in l.tops:
+                    T[t] = T[l.bottoms[0]]
+                continue
+            x = T[l.bottoms[0]]
+            if kind == "conv1":
+                n, _, h, w = x.shape
+                out = self._alloc_out(l.tops[0], n, h, w, s["cout"])
+                L.call("shf_conv1_c3", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
+                       int(s["relu"]), st)
+            elif kind == "conv":
+                if x.c_off != 0 or x.c != x.ctot:
+                    raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
+                out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"])
+                L.call("shf_conv_igemm", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
+                       s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), st)
+            elif kind == "pool":
+                out = self._alloc_out(l.tops[0], x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c)
+                L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, st)
+            elif kind == "deconv":
+                ho = s["s"] * (x.h - 1) + s["k"] - 2 * s["pad"]
+                wo = s["s"] * (x.w - 1) + s["k"] - 2 * s["pad"]
+                out = self._alloc_out(l.tops[0], x.n, ho, wo, x.c)
+                L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
+                       s["pad"], out.ctot, out.c_off, st)
+            self.launches += 1
+        if self.tail is None:
+            return None
+        return self._run_tail(im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh)
+
+    def _run_tail(self, im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh):
+        t = self.tail
+        T = self.tensors
+        dev = self.device
+        A, Cf = t["A"], t["C"]
+        feats = [T[f] for f in t["feats"]]
+        f0 = feats[0]
+        if f0.n != 1:
+            raise L.ShfError("the ProposalLayer supports single-image batches only (proposal_layer.py:74-75)")
+        H, W = f0.h, f0.w
+        hw, n = H * W, H * W * A
+        key = ("tailbuf", n)
+        buf = getattr(self, "_tailbuf", None)
+        if buf is None or buf["n"] != n:
+            ws_bytes = int(L.load().shf_sort_keys_workspace(n))
+            topn = self.cfg["pre_nms_topn"] if self.cfg["pre_nms_topn"] > 0 else n
+            buf = dict(n=n, prob=torch.empty((2 * A, H, W), dtype=torch.float32, device=dev),
+                       delta=torch.empty((4 * A, H, W), dtype=torch.float32, device=dev),
+                       boxes=torch.empty((n, 4), dtype=torch.float32, device=dev),
+                       keys=torch.empty((n,), dtype=torch.int64, device=dev),
+                       skeys=torch.empty((n,), dtype=torch.int64, device=dev),
+                       meta=torch.zeros((4,), dtype=torch.int64, device=dev),      # [count|rows], best_key
+                       ws=torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev), ws_bytes=ws_bytes,
+                       out_boxes=torch.empty((min(topn, n), 5), dtype=torch.float32, device=dev),
+                       out_probs=torch.empty((min(topn, n), 2), dtype=torch.float32, device=dev), topn=min(topn, n))
+            self._tailbuf = buf
+        st = _stream()
+        fp = (C.c_void_p * A)(*[f.t.data_ptr() for f in feats])
+        anchors = t["anchors"]
+        ap = anchors.ctypes.data_as(C.POINTER(C.c_float))
+        meta32 = buf["meta"].view(torch.int32)
+        count_ptr = C.c_void_p(buf["meta"].data_ptr())
+        rows_ptr = C.c_void_p(buf["meta"].data_ptr() + 4)
+        best_ptr = C.c_void_p(buf["meta"].data_ptr() + 8)
+        im_h, im_w, im_scale = float(im_info[0]), float(im_info[1]), float(im_info[2])
+        min_size = float(F32(self.cfg["min_size"]) * F32(im_scale))
+        L.call("shf_head_decode", fp, A, _ptr(t["wc"]), _ptr(t["bc"]), _ptr(t["wb"]), _ptr(t["bb"]), ap, H, W, Cf,
+               t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])), _ptr(buf["prob"]), _ptr(buf["delta"]),
+               _ptr(buf["boxes"]), _ptr(buf["keys"]), count_ptr, best_ptr, st)
+        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), n, _ptr(buf["ws"]), buf["ws_bytes"], st)
+        L.call("shf_proposal_gather", _ptr(buf["skeys"]), count_ptr, best_ptr, _ptr(buf["prob"]), _ptr(buf["boxes"]), A,
+               hw, buf["topn"], _ptr(buf["out_boxes"]), _ptr(buf["out_probs"]), rows_ptr,
+               _ptr(dets), _ptr(pass_offsets), int(pass_idx), int(det_cap), int(bool(flip)), float(F32(im_w)),
+               float(F32(im_scale)), float(F32(det_thresh)), st)
+        self.launches += 5       # memset x2 inside head_decode are not kernels; decode + sort (>=2) + gather
+        T[t["cls_blob"]] = buf["prob"].view(1, 2 * A, H, W)
+        T[t["box_blob"]] = buf["delta"].view(1, 4 * A, H, W)
+        return buf["out_boxes"], buf["out_probs"], meta32[1:2]
+
+    # -- blob access ---------------------------------------------------------------------------------------
+    def blob_nchw(self, name: str) -> torch.Tensor:
+        """fp32 NCHW device tensor for a materialised blob (what ``Blob.data`` exposes in Caffe)."""
+        if name not in self.tensors:
+            if self.tail and name in self._fused_tail_blobs():
+                raise L.ShfError("blob %r is fused into the detection-tail kernel and never materialised" % name)
+            raise KeyError(name)
+        t = self.tensors[name]
+        return t.to_nchw() if isinstance(t, H2) else t
+
+    def _fused_tail_blobs(self):
+        names = set()
+        for l in self.spec.layers:
+            if l.name in self.tail["fused"]:
+                names.update(l.tops)
+        return names - {self.tail["cls_blob"], self.tail["box_blob"]}

@@ -1,0 +1,310 @@
+"""Per-kernel parity on the B200: every CUDA entry point of libshf_b200.so against the CPU oracle
+(oracle/*.py) on the same seeded inputs, called through the C ABI (smallhardface_b200.lib)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():          # collected on the CPU box too; every test here needs the device
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from oracle import layers as OL
+from oracle import postprocess as OP
+from oracle import preprocess as OPRE
+from oracle import proposal as OPROP
+from smallhardface_b200 import lib as L
+from smallhardface_b200.engine import H2, _ptr, _stream, pack_conv_weights, split_h2_np
+
+DEV = torch.device("cuda:0")
+F32 = np.float32
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def h2_roundtrip_np(x):
+    hi, lo = split_h2_np(x)
+    return hi.astype(F32) + lo.astype(F32)
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(1e-30, np.abs(b).max()))
+
+
+def test_library_loads_and_reports_b200():
+    lib = L.load()
+    assert lib.shf_abi_version() == 1
+    sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+    L.call("shf_device_info", 0, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem))
+    assert maj.value == 10, "built for sm_100a only"
+    assert sm.value >= 100
+
+
+def test_h2_roundtrip():
+    x = (np.random.RandomState(0).randn(2, 24, 9, 13) * 50).astype(F32)
+    t = H2.from_nchw(dev(x))
+    back = t.to_nchw().cpu().numpy()
+    assert np.array_equal(back, h2_roundtrip_np(x))
+    assert relerr(back, x) < 2 ** -21
+
+
+def test_conv1_c3_matches_oracle():
+    rng = np.random.RandomState(1)
+    x = (rng.rand(1, 3, 37, 53) * 255 - 110).astype(F32)
+    w = (rng.randn(64, 3, 3, 3) * 0.27).astype(F32)
+    b = (rng.randn(64) * 0.05).astype(F32)
+    out = H2.empty(1, 37, 53, 64, DEV)
+    L.call("shf_conv1_c3", _ptr(dev(x)), _ptr(dev(w)), _ptr(dev(b)), _ptr(out.t), 1, 37, 53, 64, 1, _stream())
+    got = out.to_nchw().cpu().numpy()
+    ref = OL.relu(OL.conv(x, w, b, pad=(1, 1)))
+    assert relerr(got, ref) < 2e-6
+
+
+CONV_CASES = [
+    # cin, cout, H, W, k, dil, ctot, coff, relu
+    (64, 64, 24, 40, 3, 1, 64, 0, 1),
+    (64, 128, 21, 35, 3, 1, 128, 0, 1),       # ragged tiles right/bottom
+    (128, 128, 30, 30, 3, 2, 128, 0, 1),      # dilated head
+    (128, 128, 30, 30, 3, 4, 128, 0, 1),
+    (512, 256, 11, 14, 1, 1, 512, 256, 1),    # 1x1 into a concat window
+    (256, 512, 16, 16, 3, 1, 512, 0, 0),      # no ReLU, long K
+    (512, 512, 8, 8, 3, 1, 512, 0, 1),        # narrow level (W <= 8 tile shape)
+    (64, 64, 5, 7, 3, 1, 64, 0, 1),           # smaller than one tile
+]
+
+
+@pytest.mark.parametrize("cin,cout,H,W,k,dil,ctot,coff,relu", CONV_CASES)
+def test_conv_igemm_matches_oracle(cin, cout, H, W, k, dil, ctot, coff, relu):
+    rng = np.random.RandomState(cin + cout + H + W + k + dil)
+    x = h2_roundtrip_np((np.abs(rng.randn(1, cin, H, W)) * 40 * (rng.rand(1, cin, H, W) > 0.4)).astype(F32))
+    w = (rng.randn(cout, cin, k, k) * np.sqrt(2.0 / (cin * k * k))).astype(F32)
+    b = (rng.randn(cout) * 0.05).astype(F32)
+    packed, kexp = pack_conv_weights(w)
+    w_eff = (packed[0].astype(F32) + packed[1].astype(F32)) * F32(2.0 ** -kexp)          # what the kernel multiplies by
+    w_eff = w_eff.reshape(k, k, cout, cin).transpose(2, 3, 0, 1)
+    assert relerr(w_eff, w) < 2 ** -20
+    xin = H2.from_nchw(dev(x))
+    out = H2(torch.zeros((2, 1, H, W, ctot), dtype=torch.float16, device=DEV), coff, cout)
+    L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), 1, H, W, cin, cout, k, dil,
+           ctot, coff, float(2.0 ** -kexp), relu, _stream())
+    torch.cuda.synchronize()
+    got = out.to_nchw().cpu().numpy()
+    pad = dil if k == 3 else 0
+    ref = OL.conv(x, w_eff, b, pad=(pad, pad), dilation=(dil, dil))
+    if relu:
+        ref = OL.relu(ref)
+    err = relerr(got, ref)
+    assert err < 3e-6, "tcgen05 conv rel err %.3e" % err
+    if ctot != cout:                                   # channels outside the window stay untouched
+        full = H2(out.t).to_nchw().cpu().numpy()
+        assert np.all(full[:, :coff] == 0) and np.all(full[:, coff + cout:] == 0)
+    # the validation kernel agrees too (it is what big-size tests lean on)
+    out2 = H2.empty(1, H, W, cout, DEV)
+    L.call("shf_debug_conv_direct", _ptr(xin.t), _ptr(dev(w_eff)), _ptr(dev(b)), _ptr(out2.t), 1, H, W, cin, cout, k,
+           dil, pad, cout, 0, relu, _stream())
+    assert relerr(out2.to_nchw().cpu().numpy(), ref) < 3e-6
+
+
+def test_conv_igemm_batch2():
+    rng = np.random.RandomState(5)
+    x = h2_roundtrip_np(np.abs(rng.randn(2, 64, 18, 20) * 10).astype(F32))
+    w = (rng.randn(64, 64, 3, 3) * 0.06).astype(F32)
+    packed, kexp = pack_conv_weights(w)
+    w_eff = ((packed[0].astype(F32) + packed[1].astype(F32)) * F32(2.0 ** -kexp)).reshape(3, 3, 64, 64).transpose(2, 3, 0, 1)
+    xin = H2.from_nchw(dev(x))
+    out = H2.empty(2, 18, 20, 64, DEV)
+    L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed)), C.c_void_p(0), _ptr(out.t), 2, 18, 20, 64, 64, 3, 1, 64, 0,
+           float(2.0 ** -kexp), 0, _stream())
+    assert relerr(out.to_nchw().cpu().numpy(), OL.conv(x, w_eff, None, pad=(1, 1))) < 3e-6
+
+
+@pytest.mark.parametrize("H,W", [(16, 32), (7, 9)])
+def test_maxpool(H, W):
+    x = h2_roundtrip_np((np.random.RandomState(2).randn(1, 64, H, W) * 30).astype(F32))
+    xin = H2.from_nchw(dev(x))
+    out = H2.empty(1, (H + 1) // 2, (W + 1) // 2, 64, DEV)
+    L.call("shf_maxpool2x2", _ptr(xin.t), _ptr(out.t), 1, H, W, 64, _stream())
+    assert np.array_equal(out.to_nchw().cpu().numpy(), OL.max_pool(x))
+
+
+def test_deconv_depthwise_into_concat_window():
+    rng = np.random.RandomState(3)
+    c, H, W = 256, 9, 11
+    x = h2_roundtrip_np(np.abs(rng.randn(1, c, H, W) * 20).astype(F32))
+    w = OL.bilinear_filler((c, 1, 4, 4)) * (1 + 0.1 * rng.rand(c, 1, 1, 1)).astype(F32)
+    xin = H2.from_nchw(dev(x))
+    dst = torch.zeros((2, 1, 2 * H, 2 * W, 512), dtype=torch.float16, device=DEV)
+    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(w)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 0, _stream())
+    got = H2(dst, 0, c).to_nchw().cpu().numpy()
+    ref = OL.deconv(x, w, None, pad=(1, 1), stride=(2, 2), group=c)
+    assert relerr(got, ref) < 1e-6
+    assert torch.all(dst[..., c:] == 0)
+
+
+@pytest.mark.parametrize("hw,scale,flip", [((224, 224), 1.0, 0), ((224, 224), 1.3671875, 1), ((96, 130), 0.29296875, 0),
+                                           ((96, 130), 2.678571428571429, 1), ((300, 200), 0.5859375, 1)])
+def test_preprocess_level_matches_cv2(hw, scale, flip):
+    from smallhardface_b200.detector import level_geometry
+    im = np.random.RandomState(3).randint(0, 256, hw + (3,)).astype(np.uint8)
+    blob = OPRE.get_image_blobs(im, [scale])[0]
+    if flip:
+        blob = np.ascontiguousarray(blob[..., ::-1])
+    ref = OPRE.pad_to_multiple(blob)
+    oh, ow, hp, wp = level_geometry(hw[0], hw[1], scale)
+    assert (oh, ow) == blob.shape[2:] and (hp, wp) == ref.shape[2:]
+    out = torch.empty((1, 3, hp, wp), dtype=torch.float32, device=DEV)
+    means = (C.c_double * 3)(*OPRE.PIXEL_MEANS.ravel())
+    L.call("shf_preprocess_level", _ptr(dev(im)), hw[0], hw[1], _ptr(out), oh, ow, hp, wp, float(scale), flip, means,
+           _stream())
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-5          # <= 1 float32 ulp of a grey level
+    assert (got != ref).mean() < 1e-3
+
+
+def _run_tail(feat_nchw, wc, bc, wb, bb, im_info, topn=10000, score_thresh=0.002):
+    """feat list (A) of (1,C,H,W) -> boxes (R,5), probs (R,2) via head_decode + sort + gather."""
+    A = len(feat_nchw)
+    _, Cc, H, W = feat_nchw[0].shape
+    n = H * W * A
+    feats = [H2.from_nchw(dev(f)) for f in feat_nchw]
+    fp = (C.c_void_p * A)(*[f.t.data_ptr() for f in feats])
+    anchors = np.ascontiguousarray(OPROP.generate_anchors(16, (1,), (1, 2, 4), (0,), (8, 8, 8)), F32)
+    prob = torch.empty((2 * A, H, W), dtype=torch.float32, device=DEV)
+    delta = torch.empty((4 * A, H, W), dtype=torch.float32, device=DEV)
+    boxes = torch.empty((n, 4), dtype=torch.float32, device=DEV)
+    keys = torch.empty((n,), dtype=torch.int64, device=DEV)
+    skeys = torch.empty((n,), dtype=torch.int64, device=DEV)
+    meta = torch.zeros((4,), dtype=torch.int64, device=DEV)
+    ws_bytes = int(L.load().shf_sort_keys_workspace(n))
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=DEV)
+    ob = torch.empty((min(topn, n), 5), dtype=torch.float32, device=DEV)
+    op = torch.empty((min(topn, n), 2), dtype=torch.float32, device=DEV)
+    cptr, rptr, bptr = (C.c_void_p(meta.data_ptr() + o) for o in (0, 4, 8))
+    L.call("shf_head_decode", fp, A, _ptr(dev(wc)), _ptr(dev(bc)), _ptr(dev(wb)), _ptr(dev(bb)),
+           anchors.ctypes.data_as(C.POINTER(C.c_float)), H, W, Cc, 8, float(im_info[0]), float(im_info[1]), 0.0,
+           float(F32(score_thresh)), _ptr(prob), _ptr(delta), _ptr(boxes), _ptr(keys), cptr, bptr, _stream())
+    L.call("shf_sort_keys", _ptr(keys), _ptr(skeys), n, _ptr(ws), ws_bytes, _stream())
+    L.call("shf_proposal_gather", _ptr(skeys), cptr, bptr, _ptr(prob), _ptr(boxes), A, H * W, min(topn, n), _ptr(ob),
+           _ptr(op), rptr, C.c_void_p(0), C.c_void_p(0), 0, 0, 0, 0.0, 1.0, 0.05, _stream())
+    R = int(meta.view(torch.int32)[1].item())
+    return ob[:R].cpu().numpy(), op[:R].cpu().numpy(), prob.cpu().numpy(), delta.cpu().numpy()
+
+
+@pytest.mark.parametrize("shared_feature,shift", [(False, -3.0), (True, -3.0), (False, -14.0)])
+def test_head_decode_sort_gather_matches_oracle(shared_feature, shift):
+    rng = np.random.RandomState(11)
+    A, Cc, H, W = 3, 128, 13, 17
+    feats = [h2_roundtrip_np(np.abs(rng.randn(1, Cc, H, W)).astype(F32)) for _ in range(1 if shared_feature else A)]
+    feats = feats * A if shared_feature else feats
+    wc = (rng.randn(A, 2, Cc) * 0.12).astype(F32)
+    bc = np.tile(np.array([0.0, shift], F32), (A, 1))
+    wb = (rng.randn(A, 4, Cc) * 0.02).astype(F32)
+    bb = (rng.randn(A, 4) * 0.01).astype(F32)
+    im_info = np.array([[H * 8 - 5, W * 8 - 3, 1.0]], F32)
+    boxes, probs, prob_map, delta_map = _run_tail(feats, wc, bc, wb, bb, im_info[0])
+    # oracle: 1x1 convs -> cls (1,2A,H,W) [bg.., fg..] / bbox (1,4A,H,W), softmax over (bg,fg), proposal
+    cls = np.zeros((1, 2 * A, H, W), F32)
+    bbx = np.zeros((1, 4 * A, H, W), F32)
+    for a in range(A):
+        s = OL.conv(feats[a], wc[a][:, :, None, None], bc[a])
+        cls[0, a], cls[0, A + a] = s[0, 0], s[0, 1]
+        bbx[0, 4 * a:4 * a + 4] = OL.conv(feats[a], wb[a][:, :, None, None], bb[a])[0]
+    sm = OL.softmax(cls.reshape(1, 2, A * H, W), 1).reshape(1, 2 * A, H, W)
+    assert np.abs(prob_map - sm[0]).max() < 2e-6
+    assert np.abs(delta_map - bbx[0]).max() < 2e-6
+    # feed the DEVICE's own probabilities/deltas to the oracle decode: isolates decode+sort+gather, which must
+    # then agree to the last bit except for expf ulps in the box sizes
+    ref_boxes, ref_probs, _ = OPROP.proposal_forward(prob_map[None], delta_map[None], im_info)
+    assert boxes.shape == ref_boxes.shape and probs.shape == ref_probs.shape
+    assert np.array_equal(probs, ref_probs)
+    assert np.abs(boxes - ref_boxes).max() < 1e-3
+    if shift < -10:
+        assert boxes.shape[0] == 1                    # nothing above SCORE_THRESH: keep the single best row
+
+
+def test_sort_ties_lower_index_first():
+    """Equal scores must come out in ascending anchor order (the oracle's stated tie rule)."""
+    A, Cc, H, W = 3, 128, 4, 5
+    feats = [np.zeros((1, Cc, H, W), F32)] * A                      # all logits equal -> all scores 0.5
+    z = np.zeros
+    boxes, probs, _, _ = _run_tail(feats, z((A, 2, Cc), F32), z((A, 2), F32), z((A, 4, Cc), F32), z((A, 4), F32),
+                                   np.array([64, 64, 1.0], F32))
+    ref_boxes, ref_probs, order = OPROP.proposal_forward(
+        np.full((1, 6, H, W), 0.5, F32), z((1, 12, H, W), F32), np.array([[64, 64, 1.0]], F32))
+    assert np.array_equal(order, np.arange(A * H * W))
+    assert np.array_equal(boxes, ref_boxes) and np.array_equal(probs, ref_probs)
+
+
+def _postprocess(dets_list, method, thresh=0.4, mode=0, out_cap=4096):
+    B = len(dets_list)
+    cap = max(1, max(len(d) for d in dets_list))
+    flat = np.zeros((B, cap, 5), F32)
+    for i, d in enumerate(dets_list):
+        flat[i, :len(d)] = d
+    seg_b = np.arange(B, dtype=np.int32) * cap
+    seg_e = seg_b + np.array([len(d) for d in dets_list], np.int32)
+    ws_bytes = int(L.load().shf_postprocess_workspace(B, cap))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=DEV)
+    oi = torch.empty((B, out_cap), dtype=torch.int32, device=DEV)
+    od = torch.empty((B, out_cap, 5), dtype=torch.float32, device=DEV)
+    oc = torch.zeros((B,), dtype=torch.int32, device=DEV)
+    L.call("shf_postprocess", _ptr(dev(flat)), _ptr(dev(seg_b)), _ptr(dev(seg_e)), B, cap, float(thresh), method, mode,
+           _ptr(oi), _ptr(od), _ptr(oc), out_cap, _ptr(ws), ws_bytes, _stream())
+    cnt = oc.cpu().numpy()
+    if method == 0:
+        return [oi[i, :cnt[i]].cpu().numpy().tolist() for i in range(B)]
+    return [od[i, :cnt[i]].cpu().numpy() for i in range(B)]
+
+
+def test_nms_indices_bit_exact_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nms.npz"))
+    tags = ["n300", "n1", "n1500", "grid"]
+    for thr in (0.4, 0.7):
+        got = _postprocess([g[t + "_dets"] for t in tags], 0, thr, mode=0)
+        for t, k in zip(tags, got):
+            assert k == g["%s_cpu_%g" % (t, thr)].tolist(), (t, thr)
+    # reference GPU kernel semantics (IoU > thresh) against the oracle restatement of nms_kernel.cu
+    got = _postprocess([g["grid_dets"], g["n300_dets"]], 0, 0.4, mode=1)
+    assert got[0] == OP.nms(g["grid_dets"], 0.4, OP.NMS_GPU) and got[1] == OP.nms(g["n300_dets"], 0.4, OP.NMS_GPU)
+    assert _postprocess([np.zeros((0, 5), F32)], 0)[0] == []
+
+
+def test_nms_host_abi_symbol(golden_dir):
+    """`_nms` with the reference's host-pointer contract (lib/nms/gpu_nms.hpp:1-2)."""
+    g = np.load(os.path.join(golden_dir, "nms.npz"))
+    d = g["n300_dets"]
+    order = np.argsort(-d[:, 4], kind="stable")
+    sd = np.ascontiguousarray(d[order])
+    keep = np.zeros(len(sd), np.int32)
+    num = C.c_int(0)
+    L.load()._nms(keep.ctypes.data_as(C.POINTER(C.c_int)), C.byref(num), sd.ctypes.data_as(C.POINTER(C.c_float)),
+                  len(sd), 5, 0.4, 0)
+    assert order[keep[:num.value]].tolist() == OP.nms(d, 0.4, OP.NMS_GPU)
+
+
+def test_bbox_vote_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bbox_vote.npz"))
+    tags = ["n0", "n1", "n2far", "n400", "n3000"]
+    got = _postprocess([g[t + "_dets"] for t in tags], 1, 0.4)
+    for t, r in zip(tags, got):
+        ref = g[t + "_vote"]
+        assert r.shape == ref.shape, t
+        assert np.abs(r[:, :4] - ref[:, :4]).max() < 1e-2        # px; measured ~1e-4 (fp32 sum order)
+        assert np.abs(r[:, 4] - ref[:, 4]).max() < 1e-6
+
+
+def test_bbox_overlaps_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bbox_overlaps.npz"))
+    b, q = g["boxes"], g["query"]
+    for kind, name in enumerate(["iou", "ioa", "itself"]):
+        out = torch.empty((len(b), len(q)), dtype=torch.float64, device=DEV)
+        L.call("shf_bbox_overlaps", _ptr(dev(b)), _ptr(dev(q)), len(b), len(q), kind, _ptr(out), _stream())
+        assert np.array_equal(out.cpu().numpy(), g[name]), name

@@ -1,0 +1,113 @@
+"""End-to-end parity on the B200: the whole deploy net and the pyramid detector against the CPU oracle.
+Tolerances are BASELINE.json's: scores 1e-3 abs, boxes 1e-2 px in raw-image coordinates."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from oracle import detect as OD
+from oracle import postprocess as OP
+from oracle.net import OracleNet
+from smallhardface_b200 import caffe_proto as cp
+from smallhardface_b200 import deploy
+from smallhardface_b200.detector import DetectConfig, Detector
+from smallhardface_b200.engine import GpuNet
+from smallhardface_b200.graph import NetSpec, load_weights
+
+DEV = torch.device("cuda:0")
+F32 = np.float32
+SCORE_TOL, BOX_TOL = 1e-3, 1e-2
+
+
+def parity_image(hw=(224, 224), seed=3):
+    return np.random.RandomState(seed).randint(0, 256, hw + (3,)).astype(np.uint8)
+
+
+def match_rows(got_boxes, got_scores, ref_boxes, ref_scores, scale=1.0):
+    """Every reference row must have a device row within the tolerances (rank swaps between near-equal
+    scores are allowed; the row sets must otherwise coincide)."""
+    assert abs(len(got_scores) - len(ref_scores)) <= max(2, len(ref_scores) // 500), (len(got_scores), len(ref_scores))
+    worst_s = worst_b = 0.0
+    used = np.zeros(len(got_scores), bool)
+    for i in range(len(ref_scores)):
+        cand = np.where((np.abs(got_scores - ref_scores[i]) < SCORE_TOL) & ~used)[0]
+        if cand.size == 0:
+            if ref_scores[i] < 0.002 + SCORE_TOL or abs(ref_scores[i] - 0.05) < SCORE_TOL:
+                continue                                   # straddles a threshold
+            raise AssertionError("no device row for reference row %d (score %.6f)" % (i, ref_scores[i]))
+        d = np.abs(got_boxes[cand] - ref_boxes[i]).max(axis=1) / scale
+        j = cand[np.argmin(d)]
+        used[j] = True
+        worst_b = max(worst_b, float(d.min()))
+        worst_s = max(worst_s, float(abs(got_scores[j] - ref_scores[i])))
+    return worst_s, worst_b
+
+
+@pytest.fixture(scope="module", params=[True, False], ids=["dilation", "standard"])
+def nets(request, tmp_path_factory):
+    d = tmp_path_factory.mktemp("deploy")
+    proto, model = deploy.write_synthetic_deployment(str(d), dilation=request.param)
+    spec = NetSpec(cp.read_net_text(proto))
+    params = load_weights(spec, cp.read_net_binary(model))
+    return request.param, proto, model, GpuNet(spec, params, "cuda:0"), OracleNet(proto, model, engine="sgemm", fast=True)
+
+
+def test_net_forward_224_blobs_and_outputs(nets):
+    dil, proto, model, gnet, onet = nets
+    im = parity_image()
+    data = np.ascontiguousarray((im.astype(F32) - np.array([[[102.9801, 115.9465, 122.7717]]])).astype(F32).transpose(2, 0, 1)[None])
+    info = np.array([[224, 224, 1.0]], F32)
+    ref = onet.forward(data=data, im_info=info)
+    boxes, probs, rows = gnet.forward(torch.from_numpy(data).to(DEV), info[0])
+    torch.cuda.synchronize()
+    R = int(rows.item())
+    report = {}
+    names = ["conv1_1", "conv1_2", "pool1", "conv2_2", "conv3_3", "pool3", "conv4_3", "conv5_3", "conv5_256",
+             "conv4_fuse", "conv4_fuse_final"] + (["conv4_fuse_final_tmp", "head_1", "head_2", "head_4"] if dil else ["head"])
+    for nm in names:
+        got = gnet.blob_nchw(nm).cpu().numpy()
+        want = onet.blobs[nm]
+        assert got.shape == want.shape, nm
+        report[nm] = float(np.abs(got - want).max() / np.abs(want).max())
+    print("per-blob max rel err:", {k: "%.2e" % v for k, v in report.items()})
+    assert max(report.values()) < 2e-5, report
+    got_prob = gnet.blob_nchw("cls_prob_reshape_output").cpu().numpy()
+    got_delta = gnet.blob_nchw("bbox_pred_output").cpu().numpy()
+    print("prob map max abs err %.2e, delta map max abs err %.2e" %
+          (np.abs(got_prob - onet.blobs["cls_prob_reshape_output"]).max(), np.abs(got_delta - onet.blobs["bbox_pred_output"]).max()))
+    assert np.abs(got_prob - onet.blobs["cls_prob_reshape_output"]).max() < SCORE_TOL
+    assert np.abs(got_delta - onet.blobs["bbox_pred_output"]).max() < 1e-4
+    gb, gp = boxes[:R].cpu().numpy(), probs[:R].cpu().numpy()
+    assert np.all(gb[:, 0] == 0) and np.all(np.diff(gp[:, 1]) <= 0)
+    ws, wb = match_rows(gb[:, 1:], gp[:, 1], ref["boxes"][:, 1:], ref["cls_prob"][:, 1])
+    print("rows %d (ref %d): worst score err %.2e, worst box err %.2e px" % (R, len(ref["boxes"]), ws, wb))
+    assert ws < SCORE_TOL and wb < BOX_TOL
+
+
+@pytest.mark.parametrize("method", ["BBOX_VOTE", "NMS"])
+def test_detector_pyramid_flip_vs_oracle(nets, method):
+    dil, proto, model, gnet, onet = nets
+    cfg = DetectConfig(scales=(100, 300, 600), nms_method=method)          # small pyramid: oracle stays in seconds
+    det = Detector(proto, model, "cuda:0", cfg)
+    im = parity_image((96, 128), seed=4)
+    dev_imgs = det.upload([im])
+    b = det.detect_device(dev_imgs)
+    got = det.download(b, 1)[0]
+    raw = det.raw_detections(b, 0)
+    probs, boxes = OD.detect_raw(onet, im, scales=cfg.scales, flip=True)
+    ref_raw = OD.threshold_dets(probs, boxes, 0.05)
+    ws, wb = match_rows(raw[:, :4], raw[:, 4], ref_raw[:, :4], ref_raw[:, 4])
+    print("%s: raw dets %d (ref %d) worst score %.2e worst box %.2e px" % (method, len(raw), len(ref_raw), ws, wb))
+    assert ws < SCORE_TOL and wb < BOX_TOL
+    # post-processing decisions are discrete: run the oracle's vote / NMS on the DEVICE's raw detections so that
+    # sub-tolerance input differences cannot flip a cluster, then require exact structure
+    if method == "BBOX_VOTE":
+        ref = OP.bbox_vote(raw.copy(), 0.4)
+        assert got.shape == ref.shape and got.dtype == np.float64
+        assert np.abs(got[:, :4] - ref[:, :4]).max() < BOX_TOL and np.abs(got[:, 4] - ref[:, 4]).max() < 1e-6
+    else:
+        keep = OP.nms(raw, 0.4, OP.NMS_CPU)
+        assert np.array_equal(got, raw[keep])
