@@ -140,7 +140,8 @@ class GpuNet:
                 if t not in l.bottoms or l.type == "Input":
                     producers[t] = l
             for b in l.bottoms:
-                consumers.setdefault(b, []).append(l)
+                if b not in l.tops:                      # in-place layers (ReLU) do not count as consumers
+                    consumers.setdefault(b, []).append(l)
         self.producers, self.consumers = producers, consumers
         fused = set()
         self.tail = None

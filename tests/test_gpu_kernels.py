@@ -23,11 +23,19 @@ DEV = torch.device("cuda:0")
 F32 = np.float32
 
 
+_KEEP = []          # device tensors passed by raw pointer must outlive the asynchronous launch
+
+
 def dev(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.to(DEV)
+    t = t.to(DEV)
+    _KEEP.append(t)
+    if len(_KEEP) > 64:
+        torch.cuda.synchronize()
+        del _KEEP[:-32]
+    return t
 
 
 def h2_roundtrip_np(x):
