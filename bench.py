@@ -1,0 +1,307 @@
+"""bench.py -- the reference's headline metric on B200: images/sec, 1024x1024 synthetic, full pyramid.
+
+One "step" = one batch of 8 synthetic 1024x1024x3 images (BASELINE.json configs[2], through the
+dilated-head deploy net of configs[3]) taken through the whole hot path: image pyramid
+(TEST.SCALES = 100..1400) x horizontal flip = 10 net forwards per image, anchor decode, score sort,
+per-pass thresholding and box voting (the reference's default NMS_METHOD).  Random-init weights of the
+exact architecture (no checkpoint ships with the reference; no network here).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, N ranks via torchrun for N>1
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm on the host cores
+
+JSON contract: see the task statement; `value` has inputs resident in HBM, `e2e` goes through
+Detector.detect() with pinned host images (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 8
+IMAGE_HW = (1024, 1024)
+WORKLOAD = "batch8_1024x1024_pyramid100-1400_flip_decode_bboxvote_dilated-heads (BASELINE configs[2]+[3])"
+
+
+def conv_flops_per_image(det, hw):
+    """Algorithmic FLOPs of the tcgen05 conv launches for one image (sum over pyramid levels x flips of
+    2*Cin*Cout*k^2*Hout*Wout) -- the numerator of roofline.achieved."""
+    from smallhardface_b200.detector import level_geometry, pyramid_scales
+    spec = det.net.spec
+    total = 0.0
+    for s in pyramid_scales(hw + (3,), det.cfg):
+        _, _, hp, wp = level_geometry(hw[0], hw[1], s, det.cfg.max_resolution)
+        shapes = spec.infer_shapes({"data": (1, 3, hp, wp)})
+        for kind, l, st in det.net.ops:
+            if kind == "conv":
+                _, co, ho, wo = shapes[l.tops[0]]
+                total += 2.0 * st["cin"] * co * st["k"] * st["k"] * ho * wo
+    return total * (2 if det.cfg.flip else 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def deploy_dir():
+    """Synthetic prototxt + caffemodel live outside the repo snapshot (they are regenerated from seed 3)."""
+    import tempfile
+    return os.path.join(tempfile.gettempdir(), "shf_b200_deploy")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def make_images(rank):
+    from smallhardface_b200 import deploy
+    return [deploy.synthetic_image(3 + rank * BATCH + i, IMAGE_HW) for i in range(BATCH)]     # seeds 3..10 on rank 0
+
+
+# -------------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(proto, model, image, levels=(0, 1, 2), threads=None):
+    """Times the oracle (the reference's algorithm: im2col + OpenBLAS sgemm per conv, separate ReLU/pool
+    passes, NumPy ProposalLayer, NumPy bbox_vote) on a bounded sample: pyramid levels `levels` (with flip)
+    of ONE image of the batch; scales the result to images/sec by the levels' share of the per-image conv
+    FLOPs.  Returns (images_per_sec, description, seconds)."""
+    from oracle import detect as OD
+    from oracle import postprocess as OP
+    from oracle import preprocess as PRE
+    from oracle.net import OracleNet
+    onet = OracleNet(proto, model, engine="sgemm", fast=True)
+    scales = PRE.pyramid_scales(image.shape)
+    t0 = time.perf_counter()
+    blobs = PRE.get_image_blobs(image, [scales[i] for i in levels])
+    all_p, all_b = [], []
+    for blob, i in zip(blobs, levels):
+        for flip in (False, True):
+            data = np.ascontiguousarray(blob[..., ::-1]) if flip else blob
+            p, b = OD.forward_level(onet, data, scales[i], flip=flip)
+            all_p.append(p); all_b.append(b)
+    dets = OD.threshold_dets(np.concatenate(all_p), np.concatenate(all_b), 0.05)
+    OP.bbox_vote(dets, 0.4)
+    dt = time.perf_counter() - t0
+    px = [PRE.pad_to_multiple(np.zeros((1, 1, int(np.rint(image.shape[0] * s)), int(np.rint(image.shape[1] * s))),
+                                       np.float32)).shape[2:] for s in scales]
+    area = np.array([h * w for h, w in px], dtype=np.float64)
+    share = area[list(levels)].sum() / area.sum()
+    ips = share / dt
+    desc = ("1 of the %d images, pyramid levels %s of %s (x flip) + decode + bbox_vote = %.1f%% of the per-image "
+            "conv FLOPs, %.1f s measured, scaled by that share" % (BATCH, [int(x) for x in np.array([100, 300, 600, 1000, 1400])[list(levels)]],
+                                                                  [100, 300, 600, 1000, 1400], 100 * share, dt))
+    return ips, desc, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the vendored Caffe cannot be built
+    in this image) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from smallhardface_b200 import deploy
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    proto, model = deploy.write_synthetic_deployment(deploy_dir(), dilation=True)
+    imgs = make_images(0)
+    times, desc = [], ""
+    for i in range(args.warmup + args.steps):
+        ips, desc, dt = cpu_baseline_sample(proto, model, imgs[i % BATCH], levels=(0, 1, 2))
+        if i >= args.warmup:
+            times.append(1.0 / ips)
+    sec_per_image = float(np.mean(times))
+    value = 1.0 / sec_per_image
+    line = {"impl": "reference", "metric": "images/sec (1024x1024 synthetic, full pyramid)", "value": value,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * sec_per_image * BATCH, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from smallhardface_b200 import deploy
+    from smallhardface_b200.detector import DetectConfig, Detector
+    from smallhardface_b200.parallel import gather_detections
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    proto, model = deploy.write_synthetic_deployment(deploy_dir(), dilation=True)
+    det = Detector(proto, model, dev, DetectConfig())
+    imgs = make_images(rank)
+    dev_imgs = det.upload(imgs)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        b = det.detect_device(dev_imgs)
+        if world > 1:
+            gather_detections(b["out_dets"], b["out_count"], world)      # the one collective: all-gather of boxes
+        return b
+
+    def step_e2e():
+        res = det.detect(imgs)                                           # pinned H2D + pipeline + D2H of boxes
+        return res
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    det.net.profile = True
+    det.net.events = []
+    launches0 = det.net.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    det.net.profile = False
+    launches = det.net.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    conv_ms = sum(a.elapsed_time(b) for a, b in det.net.events)
+    n_conv = len(det.net.events)
+    det.net.events = []
+    # e2e: same steps through the public API with host images
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_out = 0
+    for _ in range(args.steps):
+        res = step_e2e()
+        n_out = sum(r.nbytes for r in res)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        flops_img = conv_flops_per_image(det, IMAGE_HW)
+        conv_flops = flops_img * BATCH * args.steps
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        value = world * BATCH * args.steps / (ms * 1e-3)
+        line = {
+            "metric": "images/sec (1024x1024 synthetic, full pyramid)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split (fp32-equivalent)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "images_per_rank": BATCH,
+                       "image": "1024x1024x3 uint8, 8-octave noise, seeds 3..", "passes_per_image": 10,
+                       "l2": "per-step working set (activations of 80 forwards, >4 GB) exceeds the 126 MB L2",
+                       "parallelism": "dp%d (images sharded, one NCCL all-gather of boxes per step)" % world},
+            "e2e": {"value": world * BATCH * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(sum(i.nbytes for i in imgs)), "d2h_bytes_per_step": int(n_out)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel<128|64> (tcgen05, all %d launches/step)" % (n_conv // max(1, args.steps)),
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peak_src + ", bf16_tflops_sustained (fp16 MMA has the bf16 rate)",
+                         "executed_tensor_tflops": 3.0 * achieved,
+                         "note": "achieved counts ALGORITHMIC conv FLOPs; the split-fp16 scheme executes 3 MMAs per "
+                                 "algorithmic MAC, so the tensor pipe runs at 3x this figure",
+                         "conv_share_of_step": conv_ms / ms if ms > 0 else None, "traffic": None},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            ips, desc, dt = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2))
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,7 @@ Initialisation (seed ``RNG_SEED`` = 3, ``configs/default.toml:7``):
     shrink them to denormals by the heads);  biases ``N(0, 0.05)``.
   * ``conv5_256_up``: the bilinear kernel the template's filler asks for (``filler.hpp:244-262``).
   * ``cls_score*``: Gaussian scaled so the (fg-bg) logit has sigma ~ 1.5 at the reference input
-    statistics, with a background bias of +6.0 -- about 2-3 % of anchors clear the 0.05 detection
+    statistics, with a background bias of +7.3 -- about 2-3 % of anchors clear the 0.05 detection
     threshold, which gives box voting / NMS a realistic few thousand candidates per image.
   * ``bbox_pred*``: Gaussian scaled for delta sigma ~ 0.25.
 The two scale constants were calibrated once with tools/calibrate_synthetic.py on the 224x224
@@ -27,10 +27,26 @@ from .graph import NetSpec, TEST
 from .models import build_test_net, splice_dim_red
 
 RNG_SEED = 3
-CLS_LOGIT_GAIN = 0.005      # multiplies the He-normal cls weights (calibrated, see module docstring)
-CLS_LOGIT_GAIN_STD = 0.009
-BBOX_DELTA_GAIN = 0.00075
-CLS_BG_BIAS = 6.0
+CLS_LOGIT_GAIN = 0.019      # multiplies the He-normal cls weights (calibrated, see module docstring)
+CLS_LOGIT_GAIN_STD = 0.034
+BBOX_DELTA_GAIN = 0.00225
+CLS_BG_BIAS = 7.3
+
+
+def synthetic_image(seed: int, hw=(1024, 1024)) -> np.ndarray:
+    """uint8 HxWx3 test image with structure at every scale (sum of 8 octaves of box-upsampled uniform
+    noise, equal weights): unlike white noise it keeps its contrast when the pyramid resizes it by
+    0.1x..1.4x, so every level produces detections, as natural images do."""
+    rng = np.random.RandomState(seed)
+    h, w = hw
+    acc = np.zeros((h, w, 3), dtype=np.float64)
+    for octave in range(8):
+        s = 1 << octave
+        small = rng.rand(-(-h // s), -(-w // s), 3)
+        acc += np.repeat(np.repeat(small, s, axis=0), s, axis=1)[:h, :w]
+    acc -= acc.min()
+    acc /= max(acc.max(), 1e-9)
+    return np.round(acc * 255.0).astype(np.uint8)
 
 
 def bilinear_kernel(shape) -> np.ndarray:

@@ -125,6 +125,8 @@ class GpuNet:
         self.device = torch.device(device)
         self.cfg = dict(pre_nms_topn=int(pre_nms_topn), score_thresh=float(score_thresh), min_size=float(min_size))
         self.launches = 0
+        self.profile = False          # bench.py: bracket every tcgen05 conv launch with CUDA events
+        self.events = []
         self._plan(params)
         self.tensors: "OrderedDict[str, object]" = OrderedDict()
 
@@ -334,8 +336,15 @@ class GpuNet:
                 if x.c_off != 0 or x.c != x.ctot:
                     raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
                 out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"])
+                if self.profile:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 L.call("shf_conv_igemm", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
                        s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), st)
+                if self.profile:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self.events.append((e0, e1))
             elif kind == "pool":
                 out = self._alloc_out(l.tops[0], x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c)
                 L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, st)

@@ -1,0 +1,234 @@
+"""The reference's plugin surface: a ``caffe.Net``-compatible object over the CUDA engine.
+
+Mirrors ``caffe/python/caffe/_caffe.cpp`` (Net ctor :109-151, Blob.reshape :244-256, zero-copy ``.data``
+views :205-242) and ``caffe/python/caffe/pycaffe.py`` (``blobs``/``inputs``/``outputs``/``params`` :24-85,
+``forward`` :88-134) for what ``lib/test.py`` touches, same names, argument meaning and error behaviour:
+
+    net = Net(prototxt, caffemodel, TEST)
+    net.blobs['data'].reshape(1, 3, H, W); net.blobs['im_info'].reshape(1, 3)
+    out = net.forward(data=ndarray, im_info=ndarray)        # {'boxes': (R,5) view, 'cls_prob': (R,2) view}
+    out['boxes'][:, [1, 3]] = w - out['boxes'][:, [3, 1]]     # in-place edits are visible through net.blobs[...].data
+
+``Blob.data`` is a writable float32 C-contiguous ndarray that aliases the blob's host mirror; reading an
+intermediate blob copies it from the device on first access after a forward (the lazy sync of
+``syncedmem.cpp:39-91``).  The forward itself never leaves the GPU; only ``boxes``/``cls_prob`` (<= 10 000
+rows) come back.  There is no CPU mode: ``set_mode_cpu()`` raises.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+
+from . import caffe_proto as cp
+from . import lib as L
+from .graph import NetSpec, TEST as _TEST, TRAIN as _TRAIN, load_weights
+
+TRAIN, TEST = _TRAIN, _TEST
+_state = {"device": 0, "mode": "gpu"}
+
+
+def set_mode_gpu():
+    _state["mode"] = "gpu"
+
+
+def set_mode_cpu():
+    raise RuntimeError("smallhardface_b200 has no CPU mode: the inference path runs on sm_100a kernels only")
+
+
+def set_device(device_id):
+    _state["device"] = int(device_id)
+    import torch
+    torch.cuda.set_device(int(device_id))
+
+
+def _hot_path_cfg():
+    """TEST.N_DETS_PER_MODULE / SCORE_THRESH / ANCHOR_MIN_SIZE as the ProposalLayer reads them at forward time
+    (``proposal_layer.py:88-92``); defaults of ``configs/default.toml`` when the reference's cfg is not importable."""
+    try:
+        from utils.get_config import cfg           # the reference's own config object, when running inside its tree
+        return dict(pre_nms_topn=int(cfg.TEST.N_DETS_PER_MODULE), score_thresh=float(cfg.TEST.SCORE_THRESH),
+                    min_size=float(cfg.TEST.ANCHOR_MIN_SIZE))
+    except Exception:
+        return dict(pre_nms_topn=10000, score_thresh=0.002, min_size=0.0)
+
+
+class Blob(object):
+    """``caffe.Blob`` look-alike: shape bookkeeping + a host mirror exposed through ``.data``."""
+
+    def __init__(self, net, name, shape):
+        self._net, self._name = net, name
+        self._host = np.zeros(tuple(int(d) for d in shape), dtype=np.float32)
+        self._stale = False            # device copy newer than the host mirror
+
+    # -- shape protocol (``_caffe.cpp:453-476``) --
+    @property
+    def shape(self):
+        return tuple(self._host.shape)
+
+    @property
+    def count(self):
+        return int(self._host.size)
+
+    def _legacy(self, i):
+        s = self._host.shape
+        if len(s) > 4:
+            raise ValueError("Cannot use legacy accessors on Blobs with > 4 axes.")        # blob.hpp:141-154
+        return int(s[i]) if i < len(s) else 1
+    num = property(lambda self: self._legacy(0))
+    channels = property(lambda self: self._legacy(1))
+    height = property(lambda self: self._legacy(2))
+    width = property(lambda self: self._legacy(3))
+
+    def reshape(self, *dims):
+        """``Blob::Reshape`` (``blob.cpp:23-51``): new shape; storage only ever grows."""
+        if len(dims) > 32:
+            raise ValueError("blob shape exceeds kMaxBlobAxes")
+        dims = tuple(int(d) for d in dims)
+        if any(d < 0 for d in dims):
+            raise ValueError("blob dimensions must be non-negative")
+        if dims != self._host.shape:
+            self._host = np.zeros(dims, dtype=np.float32)
+        return None
+
+    @property
+    def data(self):
+        if self._stale:
+            self._net._sync_blob(self)
+        return self._host
+
+    @property
+    def diff(self):
+        raise RuntimeError("inference-only Net: blobs carry no diff")
+
+
+class Net(object):
+    """``caffe.Net(prototxt, caffemodel, phase)`` -- the legacy positional constructor ``lib/test.py:231`` uses."""
+
+    def __init__(self, network_file, weights=None, phase=TEST, level=0, stages=None):
+        if isinstance(weights, int) and phase == TEST and not isinstance(weights, bool):
+            weights, phase = None, weights                    # Net(file, phase) form
+        net_param = cp.read_net_text(str(network_file))          # raises "Could not open file ..." like CheckFile
+        self._spec = NetSpec(net_param, int(phase))
+        model = cp.read_net_binary(str(weights)) if weights is not None else cp.Msg("NetParameter")
+        self._params = load_weights(self._spec, model)
+        if int(phase) != TEST:
+            raise RuntimeError("only the TEST phase (inference) is implemented")
+        from .engine import GpuNet
+        self._engine = GpuNet(self._spec, self._params, "cuda:%d" % _state["device"], **_hot_path_cfg())
+        shapes = self._spec.infer_shapes({})
+        self.blobs = OrderedDict((n, Blob(self, n, shapes[n])) for n in self._spec.blob_names)
+        self.inputs = list(self._spec.inputs)
+        self.outputs = list(self._spec.outputs)
+        self._layer_names = [l.name for l in self._spec.layers]
+        self.top_names = OrderedDict((l.name, list(l.tops)) for l in self._spec.layers)
+        self.bottom_names = OrderedDict((l.name, list(l.bottoms)) for l in self._spec.layers)
+        self.params = OrderedDict()
+        for l in self._spec.layers:
+            if l.param_keys:
+                self.params[l.name] = [_ParamBlob(self._params[k]) for k in l.param_keys]
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, blobs=None, start=None, end=None, **kwargs):
+        """``pycaffe.py:88-134`` _Net_forward (whole-net form)."""
+        if start is not None or end is not None:
+            raise NotImplementedError("partial forward(start=, end=) is not on the inference hot path")
+        import torch
+        if kwargs:
+            if set(kwargs.keys()) != set(self.inputs):
+                raise Exception("Input blob arguments do not match net inputs.")
+            for in_, blob in kwargs.items():
+                if blob.shape[0] != self.blobs[in_].shape[0]:
+                    raise Exception("Input is not batch sized")
+                self.blobs[in_].data[...] = blob                 # broadcasting assignment, as pycaffe
+        cfgv = _hot_path_cfg()
+        self._engine.cfg.update(cfgv)
+        data_blob = self.blobs[self.inputs[0]]
+        info = self.blobs[self.inputs[1]]._host.reshape(-1) if len(self.inputs) > 1 else np.array([0, 0, 1], np.float32)
+        n, c, h, w = data_blob.shape
+        if (h % 16) or (w % 16):
+            # concat_layer.cpp:40-44 would fail the same way inside Caffe's Reshape
+            self._spec.infer_shapes({self.inputs[0]: data_blob.shape})
+        dev = self._engine.device
+        host = torch.from_numpy(data_blob._host)
+        data_dev = host.pin_memory().to(dev, non_blocking=True)
+        res = self._engine.forward(data_dev, (float(info[0]), float(info[1]), float(info[2])))
+        for b in self.blobs.values():
+            b._stale = True
+        for name in self.inputs:
+            self.blobs[name]._stale = False
+        if res is not None:
+            boxes, probs, rows = res
+            R = int(rows.item())                               # the one device->host sync of the forward
+            tops = self._engine.tail["tops"]
+            self._set_host(tops[0], boxes[:R].cpu().numpy())
+            if len(tops) > 1:
+                self._set_host(tops[1], probs[:R].cpu().numpy())
+        outs = set(self.outputs + list(blobs or []))
+        return {out: self.blobs[out].data for out in outs}
+
+    __call__ = forward
+
+    def _set_host(self, name, arr):
+        b = self.blobs[name]
+        b._host = np.ascontiguousarray(arr, dtype=np.float32)
+        b._stale = False
+
+    def _sync_blob(self, blob):
+        t = self._engine.blob_nchw(blob._name)                   # raises for blobs fused away inside a kernel
+        blob._host = np.ascontiguousarray(t.cpu().numpy().reshape(blob._net._current_shape(blob._name, t)))
+        blob._stale = False
+
+    def _current_shape(self, name, t):
+        return tuple(t.shape)
+
+    @property
+    def layer_dict(self):
+        return OrderedDict((l.name, l) for l in self._spec.layers)
+
+    def save(self, filename):
+        from .deploy import params_to_netparameter
+        cp.write_net_binary(str(filename), params_to_netparameter(self._spec, self._params))
+
+
+class _ParamBlob(object):
+    def __init__(self, arr):
+        self.data = arr
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+
+class Layer(object):
+    """``caffe.Layer`` base for Python layers (``python_layer.hpp:19-43``).  The only Python layer on the test
+    path, ``lib.layers.proposal_layer.ProposalLayer``, is executed by the fused CUDA tail and never instantiated."""
+
+    def setup(self, bottom, top):
+        pass
+
+    def reshape(self, bottom, top):
+        pass
+
+    def forward(self, bottom, top):
+        pass
+
+    def backward(self, top, propagate_down, bottom):
+        pass
+
+
+def _training_only(name):
+    def _raise(*a, **k):
+        raise RuntimeError("caffe.%s belongs to the training path, which is out of scope for this build" % name)
+    return _raise
+
+
+# referenced by lib/train.py at import/definition time only
+SGDSolver = _training_only("SGDSolver")
+NCCL = _training_only("NCCL")
+set_random_seed = lambda seed: None
+set_solver_count = _training_only("set_solver_count")
+set_solver_rank = _training_only("set_solver_rank")
+set_multiprocess = _training_only("set_multiprocess")
+init_log = lambda *a, **k: None
+log = lambda *a, **k: None

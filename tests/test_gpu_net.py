@@ -92,7 +92,7 @@ def test_detector_pyramid_flip_vs_oracle(nets, method):
     dil, proto, model, gnet, onet = nets
     cfg = DetectConfig(scales=(100, 300, 600), nms_method=method)          # small pyramid: oracle stays in seconds
     det = Detector(proto, model, "cuda:0", cfg)
-    im = parity_image((96, 128), seed=4)
+    im = deploy.synthetic_image(4, (96, 128))               # multi-octave noise: detections at every level
     dev_imgs = det.upload([im])
     b = det.detect_device(dev_imgs)
     got = det.download(b, 1)[0]

@@ -1,0 +1,197 @@
+"""CPU-side checks of the product's host logic and of the drop-in boundary: the C-ABI library loads and
+exports every symbol include/shf_b200.h declares (no compute calls without a GPU), the `caffe` /
+`caffe.proto.caffe_pb2` shims behave, the py2 source hook handles the reference's files, and the host scalar
+logic (pyramid scales, level geometry, anchors, shard ranges) equals the oracle's restatement."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from smallhardface_b200 import caffe_proto as cp
+from smallhardface_b200 import lib as L
+from smallhardface_b200.models import build_test_net, splice_dim_red
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "shf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(shf_\w+|_nms)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    if not os.path.exists(L.LIB_PATH):
+        L.build()
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.shf_abi_version() == 1                    # a plain host function: safe without a GPU
+    assert lib.shf_last_error() is not None
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.ShfError, match="no CPU fallback"):
+        L.load()
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "smallhardface_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_pyramid_and_geometry_match_oracle():
+    from oracle import preprocess as P
+    from smallhardface_b200.detector import DetectConfig, compute_scaling_factor, level_geometry, pyramid_scales
+    cfg = DetectConfig()
+    for shape in [(1024, 1024, 3), (768, 1024, 3), (1024, 683, 3), (500, 1024, 3), (224, 224, 3), (97, 1301, 3)]:
+        assert pyramid_scales(shape, cfg) == P.pyramid_scales(shape)
+        assert compute_scaling_factor(shape, 800, 1200) == P.compute_scaling_factor(shape, 800, 1200)
+        for s in pyramid_scales(shape, cfg):
+            oh, ow, hp, wp = level_geometry(shape[0], shape[1], s)
+            assert (oh, ow) == (int(np.rint(shape[0] * s)), int(np.rint(shape[1] * s)))
+            assert hp % 16 == 0 and wp % 16 == 0 and 0 <= hp - oh < 16 and 0 <= wp - ow < 16
+    assert [level_geometry(1024, 1024, s)[2] for s in pyramid_scales((1024, 1024, 3), cfg)] == [112, 304, 608, 1008, 1408]
+
+
+def test_anchors_match_reference_golden(golden_dir):
+    from smallhardface_b200.anchors import generate_anchors
+    g = np.load(os.path.join(golden_dir, "anchors.npz"))
+    assert np.array_equal(generate_anchors(16, (1,), (1, 2, 4), (0,), (8, 8, 8)), g["anchors"])
+    assert np.array_equal(generate_anchors(strides=(16, 16, 16)), g["default"])
+
+
+def test_shard_range_is_the_reference_partition():
+    from smallhardface_b200.parallel import shard_range
+    for n, g in [(3226, 8), (3226, 4), (10, 4), (3, 8), (8, 8)]:
+        per = int(np.ceil(1. * n / g))                                   # lib/test.py:329
+        got = [shard_range(n, g, r) for r in range(g)]
+        assert got == [(min(per * r, n), min(per * (r + 1), n)) for r in range(g)]
+        assert sum(b - a for a, b in got) == n
+
+
+def test_weight_packing_is_exact_to_22_bits():
+    from smallhardface_b200.engine import pack_conv_weights
+    w = (np.random.RandomState(0).randn(128, 64, 3, 3) * 0.03).astype(np.float32)
+    packed, k = pack_conv_weights(w)
+    assert packed.shape == (2, 9, 128, 64) and packed.dtype == np.float16
+    back = (packed[0].astype(np.float32) + packed[1].astype(np.float32)) * np.float32(2.0 ** -k)
+    back = back.reshape(3, 3, 128, 64).transpose(2, 3, 0, 1)
+    assert np.abs(back - w).max() <= 2.0 ** -21 * np.abs(w).max()
+    assert np.isfinite(packed.astype(np.float32)).all()
+
+
+# ---- caffe / caffe_pb2 shims ---------------------------------------------------------------------
+def test_caffe_pb2_shim_text_and_wire():
+    from smallhardface_b200 import compat
+    compat.install()
+    import caffe
+    from caffe.proto import caffe_pb2
+    import google.protobuf.text_format as txtf
+    assert (caffe.TRAIN, caffe.TEST) == (0, 1)
+    with pytest.raises(RuntimeError):
+        caffe.set_mode_cpu()
+    txt = cp.format_text(build_test_net(True))
+    pb = caffe_pb2.NetParameter()
+    txtf.Merge(txt, pb)
+    assert len(pb.layer) == 55 and pb.layer[-1].python_param.layer == "ProposalLayer"
+    assert pb.layer[0].convolution_param.bias_term is True              # proto2 default survives
+    assert pb.SerializeToString() == cp.encode(cp.parse_text(txt))       # same bytes as the hand-written codec
+    assert cp.format_text(cp.parse_text(str(pb))) == txt
+
+
+def test_caffe_pb2_supports_what_manipulate_py_does():
+    """lib/prototxt/manipulate.py:98-188 restated call by call on the shim classes."""
+    from smallhardface_b200 import compat
+    compat.install()
+    from caffe.proto import caffe_pb2
+    import google.protobuf.text_format as txtf
+    pb = caffe_pb2.NetParameter()
+    txtf.Merge(cp.format_text(build_test_net(True)), pb)
+    split = min(i for i, x in enumerate(pb.layer) if x.name.startswith("head"))
+    pb.layer[split - 2].top[0] += "_tmp"
+    pb.layer[split - 1].bottom[0] += "_tmp"
+    pb.layer[split - 1].top[0] += "_tmp"
+    conv = caffe_pb2.LayerParameter()
+    conv.name, conv.type = "conv4_fuse_final_dim_red", "Convolution"
+    conv.bottom.append("conv4_fuse_final_tmp"); conv.top.append("conv4_fuse_final")
+    conv.convolution_param.num_output = 128
+    conv.convolution_param.pad.append(1); conv.convolution_param.kernel_size.append(3)
+    conv.convolution_param.weight_filler.type = "gaussian"; conv.convolution_param.weight_filler.std = 0.01
+    conv.convolution_param.bias_filler.type = "constant"; conv.convolution_param.bias_filler.value = 0.0
+    conv.convolution_param.dilation.append(1)
+    conv.ClearField("param")
+    conv.param.extend([caffe_pb2.ParamSpec()] * 2)
+    conv.param[0].lr_mult = 1.0; conv.param[0].decay_mult = 1.0
+    conv.param[1].lr_mult = 2.0; conv.param[1].decay_mult = 1.0
+    relu = caffe_pb2.LayerParameter()
+    relu.name, relu.type = "conv4_fuse_final_dim_red_relu", "ReLU"
+    relu.bottom.append("conv4_fuse_final"); relu.top.append("conv4_fuse_final")
+    new_layers = pb.layer[:split] + [conv, relu] + pb.layer[split:]
+    pb.ClearField("layer")
+    pb.layer.extend(new_layers)
+    assert cp.format_text(cp.parse_text(str(pb))) == cp.format_text(splice_dim_red(build_test_net(True)))
+
+
+# ---- py2 hook --------------------------------------------------------------------------------------
+def test_py2_transform_units():
+    from smallhardface_b200.compat.py2hook import transform_source as T
+    assert "print('a', b)" in T("print 'a', b\n")
+    assert "print(x, end=' ')" in T("print x,\n")
+    assert "print('f: {}'.format(s))" in T("    print 'f: {}'.format(s)\n")
+    assert "range(3)" in T("for i in xrange(3): pass\n")
+    assert "(k in d)" in T("if d.has_key(k): pass\n")
+    assert ".items()" in T("for a, b in d.iteritems(): pass\n")
+    assert "import pickle" in T("import cPickle\n")
+    assert "'xrange'" in T("s = 'xrange'\n")                          # strings untouched
+    assert "except ValueError as e:" in T("try:\n    pass\nexcept ValueError, e:\n    pass\n")
+    assert T("from __future__ import print_function\nprint('x', end='')\n").count("print('x', end='')") == 1
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+def test_reference_python_files_import_unmodified_through_the_hook(tmp_path, monkeypatch):
+    import glob
+    from smallhardface_b200 import compat
+    from smallhardface_b200.compat import py2hook
+    for f in glob.glob(REF + "/lib/**/*.py", recursive=True) + [REF + "/train_test.py"]:
+        compile(py2hook.transform_source(open(f).read(), f), f, "exec")
+    # the config module asserts configs/default.toml relative to the CWD (get_config.py:24-27)
+    os.symlink(REF + "/configs", tmp_path / "configs")
+    os.symlink(REF + "/models", tmp_path / "models")
+    monkeypatch.chdir(tmp_path)
+    for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k.startswith("lib.") or k == "lib"]:
+        del sys.modules[k]
+    compat.install(REF)
+    try:
+        from utils.get_config import cfg
+        assert list(cfg.TEST.SCALES) == [100, 300, 600, 1000, 1400] and cfg.TEST.NMS_METHOD == "BBOX_VOTE"
+        from lib.layers.generate_anchors import generate_anchors
+        a = generate_anchors(scales=np.array([1, 2, 4]), base_size=16, ratios=np.array([1]), shifts=np.array([0]),
+                             strides=np.array([8, 8, 8]))
+        assert a.tolist() == [[0, 0, 15, 15], [-8, -8, 23, 23], [-24, -24, 39, 39]]
+        from utils.test_utils import _compute_scaling_factor
+        from smallhardface_b200.detector import compute_scaling_factor
+        assert _compute_scaling_factor((768, 1024, 3), 800, 1200) == compute_scaling_factor((768, 1024, 3), 800, 1200)
+        import utils.cython_bbox as cb                                    # our drop-in shadows the unbuilt .pyx
+        assert cb.__name__.endswith("cython_bbox") and hasattr(cb, "bbox_overlaps_IoA")
+        # the reference's own prototxt rewriting runs on the caffe_pb2 shim
+        cfg.MODEL.DIFFERENT_DILATION.ENABLE = True
+        from lib.prototxt import manipulate
+        out = tmp_path / "test.prototxt"
+        manipulate.manipulate_test("models/test_template.prototxt", str(out))
+        assert cp.format_text(cp.read_net_text(str(out))) == cp.format_text(splice_dim_red(build_test_net(True)))
+    finally:
+        sys.meta_path[:] = [f for f in sys.meta_path if not isinstance(f, py2hook.Py2Finder)]
+        sys.path[:] = [p for p in sys.path if not p.startswith(REF)]
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k.startswith("lib.") or k == "lib"]:
+            del sys.modules[k]
