@@ -34,6 +34,10 @@ int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void*
                    int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                    float out_scale, int relu, void* stream);
 
+/* Tuning / test hook: selects the operand-staging strategy of shf_conv_igemm (same results, different smem traffic):
+ * 0 = one TMA load per (tap, chunk); 1 = halo tile reused by all taps (default); 2-4 = halo variants under test. */
+int shf_set_conv_impl(int impl);
+
 /* conv1_1: fp32 NCHW (N,3,H,W) [dev] -> h2 (N,H,W,64); weights OIHW fp32 [dev] (64,3,3,3), pad 1. */
 int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch, int H, int W,
                  int cout, int relu, void* stream);

@@ -17,6 +17,7 @@
 //   roles   : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 bias loader,
 //             warps 4-7 epilogue (TMEM -> registers -> bias/ReLU/split -> swizzled smem -> TMA store)
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -230,42 +231,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // -------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-int encode_f16_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box, const char* what) {
-  EncodeTiledFn fn = get_encode_fn();
-  SHF_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-  cuuint64_t gdim[5], gstride[4];
-  cuuint32_t bdim[5], estride[5];
-  uint64_t stride = 2;
-  for (int i = 0; i < rank; ++i) {
-    gdim[i] = dims[i];
-    bdim[i] = box[i];
-    estride[i] = 1;
-    stride *= dims[i];
-    if (i < rank - 1) gstride[i] = stride;
-  }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, gdim, gstride, bdim, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SHF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
-  return 0;
-}
-
 template <int BN>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, int batch,
                 cudaStream_t stream) {
@@ -284,8 +249,8 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 }  // namespace
 
-// C ABI -- see include/shf_b200.h
-extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H,
+// v1 (one TMA load per tap); the public shf_conv_igemm in conv_halo.cu dispatches here when asked to
+int shf_conv_pertap_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H,
                               int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
                               int out_channel_offset, float out_scale, int relu, void* stream) {
   SHF_REQUIRE(ksize == 3 || ksize == 1, "shf_conv_igemm: kernel size %d (only 3x3 and 1x1 are on the hot path)", ksize);
@@ -317,17 +282,17 @@ extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* 
   {
     uint64_t d[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)batch, 2};
     uint32_t b[5] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1, 2};
-    if (int e = encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "activations")) return e;
+    if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "activations")) return e;
   }
   {
     uint64_t d[4] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)taps, 2};
     uint32_t b[4] = {64, (uint32_t)bn, 1, 2};
-    if (int e = encode_f16_map(&tb, const_cast<void*>(w_h2), 4, d, b, "weights")) return e;
+    if (int e = shf_encode_f16_map(&tb, const_cast<void*>(w_h2), 4, d, b, "weights")) return e;
   }
   {
     uint64_t d[5] = {(uint64_t)out_channels_total, (uint64_t)W, (uint64_t)H, (uint64_t)batch, 2};
     uint32_t b[5] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1, 1};
-    if (int e = encode_f16_map(&to, out_h2, 5, d, b, "output")) return e;
+    if (int e = shf_encode_f16_map(&to, out_h2, 5, d, b, "output")) return e;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return bn == 128 ? launch_conv<128>(ta, tb, to, p, batch, st) : launch_conv<64>(ta, tb, to, p, batch, st);
