@@ -244,7 +244,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_5d(&tmap_o, smem_base + (uint32_t)(pl * (BN / 64) + t) * (kTileM * 128),
                        p.cout_offset + n0 + t * 64, x0, y0, img, pl);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();       // smem may be released once the bulk store has read it; the writes drain on their own
     }
   }
   tc_fence_before();
