@@ -24,6 +24,10 @@ int shf_conv_pertap_impl(const void* in_h2, const void* w_h2, const float* bias,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* stream);
 
+int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
+                         int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
+                         float out_scale, int relu, void* stream);
+
 namespace {
 
 constexpr int kTileM = 128;
@@ -258,9 +262,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // implementation selector (shf_set_conv_impl; tests / tuning):
 //   0 = v1 per-tap loads (conv_igemm.cu)      1 = halo, XW = 16        3 = halo, XW = 8 + 2d (default)
 //   5 = as 3 but 64-channel N tiles whenever Cout <= 128 (two CTAs per SM)
+//   7 = v3 persistent streaming-drain kernel (conv_stream.cu)
 //   2 / 4 = as 1 / 3 with descriptor base_offset = (start >> 7) & 7 -- measured WRONG on B200: the UMMA swizzle is a
 //           function of the absolute smem address, base_offset must stay 0 (kept only as a regression probe)
-int g_conv_impl = 3;
+int g_conv_impl = 7;
 
 template <int BN>
 int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HaloParams& p, int batch,
@@ -279,7 +284,7 @@ int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 }  // namespace
 
 extern "C" int shf_set_conv_impl(int impl) {
-  SHF_REQUIRE(impl >= 0 && impl <= 5, "shf_set_conv_impl: %d", impl);
+  SHF_REQUIRE(impl >= 0 && impl <= 7, "shf_set_conv_impl: %d", impl);
   g_conv_impl = impl;
   return 0;
 }
@@ -288,6 +293,9 @@ extern "C" int shf_set_conv_impl(int impl) {
 extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H,
                               int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
                               int out_channel_offset, float out_scale, int relu, void* stream) {
+  if (g_conv_impl == 7)
+    return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
+                                out_channel_offset, out_scale, relu, stream);
   if (g_conv_impl == 0)
     return shf_conv_pertap_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                                 out_channel_offset, out_scale, relu, stream);

@@ -1,0 +1,330 @@
+// Implicit-GEMM convolution v3 on tcgen05 tensor cores (sm_100a): persistent CTAs, halo-tile operand reuse, and
+// accumulators that are DRAINED into registers every few dozen MMAs while the tensor pipe keeps running.
+//
+// Same math / layout / reference citations as conv_igemm.cu and conv_halo.cu.  What v3 changes, and why
+// (numbers from profiles/r01_*):
+//  * persistent: one CTA per SM walks tiles t = blockIdx.x + i*gridDim.x.  v2 paid ~15k cycles per tile for CTA
+//    launch, barrier init, TMEM alloc, first-load latency and a serial epilogue; here the TMA rings simply keep
+//    running into the next tile and the epilogue of tile i overlaps the main loop of tile i+1.
+//  * N-stacked MMAs: the weight stage is [B_hi ; B_lo] (2*BN rows), so  A_hi x [B_hi;B_lo]  is ONE N = 2*BN MMA
+//    that yields hi*hi in columns [0,BN) and hi*lo in [BN,2BN); a second N = BN MMA adds A_lo x B_hi to the
+//    cross columns.  8 MMAs per stage instead of 12 (the single issuing thread was the bottleneck), A_hi is read
+//    from shared memory once instead of twice.
+//  * streaming drain: tensor memory holds two accumulator sets of 2*BN columns.  The MMA issuer alternates sets
+//    every "phase" (= the 9 taps of one 64-channel chunk: 36 k-steps); the four epilogue warps add the finished
+//    set into fp32 registers with round-to-nearest and hand it back.  The tensor core truncates when it aligns
+//    products to a running accumulator, so its error grows with the accumulation count: a phase is 36
+//    accumulations against 96 (v2) or 864 (a single accumulator over K = 4608).
+//  * epilogue writes NHWC hi/lo rows straight from registers (each thread owns one pixel: 2*BN contiguous bytes
+//    per plane), so no staging buffer competes with the operand rings for shared memory.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tma_host.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kTH = 16, kTW = 8;
+constexpr int kChunkK = 64;
+constexpr int kMaxA = 4, kMaxB = 6;
+
+struct StreamParams {
+  int H, W, batch;
+  int cin_chunks, taps, dil, pad;
+  int xw, xh;                 // halo width / height (pixels)
+  int na, nb;                 // ring depths
+  int a_bytes, a_tx, b_bytes;
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  int chunks_per_phase;       // G
+  int ctot, cout_offset, relu;
+  float out_scale;
+  const float* bias;
+  __half* out;                // h2 destination tensor base (plane 0); plane 1 at + plane_elems
+  long long plane_elems;
+};
+
+SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const StreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int pipe_bytes = p.na * p.a_bytes + p.nb * p.b_bytes;
+  // barriers: fullA[4] emptyA[4] fullB[6] emptyB[6] accFull[2] accEmpty[2]
+  const uint32_t bar_base = smem_base + (uint32_t)pipe_bytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + 8 * (2 * kMaxA + 2 * kMaxB + 4));
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto empty_a = [&](int s) { return bar_base + 8u * (kMaxA + s); };
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
+  auto empty_b = [&](int s) { return bar_base + 8u * (2 * kMaxA + kMaxB + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxA + 2 * kMaxB + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxA + 2 * kMaxB + 2 + s); };
+  auto a_stage = [&](int s) { return smem_base + (uint32_t)(s * p.a_bytes); };
+  auto b_stage = [&](int s) { return smem_base + (uint32_t)(p.na * p.a_bytes + s * p.b_bytes); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 512;          // whole tensor memory: two sets of 2*BN columns at fixed addresses
+  constexpr uint32_t kSetCols = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kMaxA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < kMaxB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (*tmem_slot != 0u) __trap();              // the full allocation starts at column 0
+  const int phases_per_tile = (p.cin_chunks + p.chunks_per_phase - 1) / p.chunks_per_phase;
+
+  // tile -> (n tile, x tile, y tile, image); n fastest so neighbouring CTAs share the activation patch in L2
+  auto decode_tile = [&](int t, int& nt, int& x0, int& y0, int& img) {
+    nt = t % p.n_tiles;
+    int q = t / p.n_tiles;
+    x0 = (q % p.tiles_x) * kTW;
+    q /= p.tiles_x;
+    y0 = (q % p.tiles_y) * kTH;
+    img = q / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight stages [B_hi ; B_lo], one per (chunk, tap) =====================
+    if (lane == 0) {
+      int itb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int nt, x0, y0, img;
+        decode_tile(t, nt, x0, y0, img);
+        for (int cc = 0; cc < p.cin_chunks; ++cc)
+          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
+            const int sb = itb % p.nb;
+            mbar_wait(empty_b(sb), ((itb / p.nb) & 1) ^ 1);
+            mbar_arrive_expect_tx(full_b(sb), p.b_bytes);
+            tma_load_4d(b_stage(sb), &tmap_b, full_b(sb), cc * kChunkK, nt * BN, tap, 0);
+          }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer: activation halos, one per 64-channel chunk =====================
+    if (lane == 0) {
+      int ita = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int nt, x0, y0, img;
+        decode_tile(t, nt, x0, y0, img);
+        for (int cc = 0; cc < p.cin_chunks; ++cc, ++ita) {
+          const int sa = ita % p.na;
+          mbar_wait(empty_a(sa), ((ita / p.na) & 1) ^ 1);
+          mbar_arrive_expect_tx(full_a(sa), p.a_tx);
+          tma_load_5d(a_stage(sa), &tmap_a, full_a(sa), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp converged, one elected lane issues) =====================
+    constexpr uint32_t idesc_wide = umma_idesc_f16(kTileM, 2 * BN);     // A_hi x [B_hi ; B_lo]
+    constexpr uint32_t idesc_half = umma_idesc_f16(kTileM, BN);         // A_lo x B_hi (and the phase-opening hi*hi)
+    const uint32_t a_hi32 = (uint32_t)((p.xw * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
+    constexpr uint32_t b_hi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t lbo = 1u << 16;
+    const uint32_t a_plane16 = ((uint32_t)(p.xh * p.xw) * 128u) >> 4;
+    const int ktaps = (p.taps == 9) ? 3 : 1;
+    int ita = 0, itb = 0, gp = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
+        const int set = gp & 1;
+        const uint32_t d_main = (uint32_t)set * kSetCols;
+        mbar_wait(acc_empty(set), ((gp >> 1) & 1) ^ 1);           // drained by the epilogue warps
+        tc_fence_after();
+        const int c_begin = ph * p.chunks_per_phase;
+        const int c_end = min(c_begin + p.chunks_per_phase, p.cin_chunks);
+        uint32_t opened = 0;                                      // 0 until the set has been overwritten once
+        for (int cc = c_begin; cc < c_end; ++cc, ++ita) {
+          const int sa = ita % p.na;
+          mbar_wait(full_a(sa), (ita / p.na) & 1);
+          const uint32_t a_base = a_stage(sa);
+          int r = 0, s = 0;
+          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
+            const int sb = itb % p.nb;
+            mbar_wait(full_b(sb), (itb / p.nb) & 1);
+            tc_fence_after();
+            const uint32_t a_off = (uint32_t)((r * p.dil) * p.xw + s * p.dil) * 128u;
+            uint32_t a_lo32 = (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo;
+            uint32_t b_lo32 = ((b_stage(sb) & 0x3FFFFu) >> 4) | lbo;
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k) {
+              // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
+              umma_f16_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
+              // cross += A_lo x B_hi
+              umma_f16_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+              opened = 1u;
+              a_lo32 += 2; b_lo32 += 2;
+            }
+            umma_commit_elect(empty_b(sb));
+            if (++s == ktaps) { s = 0; ++r; }
+          }
+          umma_commit_elect(empty_a(sa));
+        }
+        umma_commit_elect(acc_full(set));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== drain + epilogue warps =====================
+    const int w = warp - 4;
+    const int m = w * 32 + lane;                 // accumulator row = pixel (y_local * 8 + x_local)
+    const uint32_t lane_addr = (uint32_t)(w * 32) << 16;
+    const float scale = p.out_scale;
+    int gp = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int nt, x0, y0, img;
+      decode_tile(t, nt, x0, y0, img);
+      float acc[BN];
+#pragma unroll
+      for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+      for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
+        const int set = gp & 1;
+        mbar_wait(acc_full(set), (gp >> 1) & 1);
+        tc_fence_after();
+        const uint32_t base = lane_addr + (uint32_t)set * kSetCols;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t mq[32], cq[32];
+          tmem_ld_32x32(base + c0, mq);            // hi*hi partial
+          tmem_ld_32x32(base + BN + c0, cq);       // cross partial
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            acc[c0 + e] = __fadd_rn(__fadd_rn(acc[c0 + e], __uint_as_float(cq[e])), __uint_as_float(mq[e]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cnt(acc_empty(set));          // 4 warps -> the set is free again
+      }
+      // ---- epilogue for this tile: bias, ReLU, split to hi/lo, NHWC rows straight to global memory ----
+      const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      if (y < p.H && x < p.W) {
+        const int n0 = nt * BN;
+        __half* dst = p.out + ((((size_t)img * p.H + y) * p.W + x) * (size_t)p.ctot + p.cout_offset + n0);
+        const float* bias = p.bias ? p.bias + n0 : nullptr;
+#pragma unroll
+        for (int c = 0; c < BN; c += 8) {
+          uint32_t hi_pk[4], lo_pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v0 = acc[c + 2 * e] * scale + (bias ? __ldg(bias + c + 2 * e) : 0.f);
+            float v1 = acc[c + 2 * e + 1] * scale + (bias ? __ldg(bias + c + 2 * e + 1) : 0.f);
+            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            __half h0, l0, h1, l1;
+            split_h2(v0, h0, l0);
+            split_h2(v1, h1, l1);
+            hi_pk[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo_pk[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+          *reinterpret_cast<uint4*>(dst + c) = make_uint4(hi_pk[0], hi_pk[1], hi_pk[2], hi_pk[3]);
+          *reinterpret_cast<uint4*>(dst + p.plane_elems + c) = make_uint4(lo_pk[0], lo_pk[1], lo_pk[2], lo_pk[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(0u, kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
+                  cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  conv_stream_kernel<BN><<<grid, 256, smem_bytes, stream>>>(ta, tb, p);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
+                         int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
+                         float out_scale, int relu, void* stream) {
+  SHF_REQUIRE(ksize == 3 || ksize == 1, "shf_conv_igemm: kernel size %d (only 3x3 and 1x1 are on the hot path)", ksize);
+  SHF_REQUIRE(cin % 64 == 0 && cin >= 64, "shf_conv_igemm: Cin=%d must be a multiple of 64", cin);
+  SHF_REQUIRE(cout % 64 == 0 && cout >= 64, "shf_conv_igemm: Cout=%d must be a multiple of 64", cout);
+  SHF_REQUIRE(out_channel_offset % 8 == 0 && out_channel_offset + cout <= out_channels_total &&
+                  out_channels_total % 8 == 0,
+              "shf_conv_igemm: bad destination channel window [%d,%d) of %d", out_channel_offset,
+              out_channel_offset + cout, out_channels_total);
+  SHF_REQUIRE(batch >= 1 && H >= 1 && W >= 1 && dilation >= 1 && dilation <= 4, "shf_conv_igemm: bad geometry");
+  const int bn = (cout % 128 == 0) ? 128 : 64;
+  StreamParams p;
+  p.H = H; p.W = W; p.batch = batch;
+  p.cin_chunks = cin / 64;
+  p.taps = ksize * ksize;
+  p.dil = (ksize == 3) ? dilation : 0;
+  p.pad = p.dil;
+  p.xw = kTW + 2 * p.pad;
+  p.xh = kTH + 2 * p.pad;
+  p.a_tx = 2 * p.xh * p.xw * 128;
+  p.a_bytes = (p.a_tx + 1023) & ~1023;
+  p.b_bytes = 2 * bn * 128;
+  const int budget = 227 * 1024 - 1024 - 512;
+  p.na = (p.taps == 1) ? kMaxA : 2;
+  while (p.na > 1 && p.na * p.a_bytes + 3 * p.b_bytes > budget) --p.na;
+  p.nb = (budget - p.na * p.a_bytes) / p.b_bytes;
+  if (p.nb > kMaxB) p.nb = kMaxB;
+  if (const char* e = getenv("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
+  SHF_REQUIRE(p.nb >= 2, "shf_conv_igemm: halo tile of %d bytes leaves no room for the weight ring", p.a_bytes);
+  p.tiles_x = (W + kTW - 1) / kTW;
+  p.tiles_y = (H + kTH - 1) / kTH;
+  p.n_tiles = cout / bn;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * batch;
+  p.chunks_per_phase = (p.taps == 9) ? 1 : 9;
+  if (const char* e = getenv("SHF_PROBE_G")) { int v = atoi(e); if (v >= 1) p.chunks_per_phase = v; }
+  p.ctot = out_channels_total;
+  p.cout_offset = out_channel_offset;
+  p.relu = relu;
+  p.out_scale = out_scale;
+  p.bias = bias;
+  p.out = reinterpret_cast<__half*>(out_h2);
+  p.plane_elems = (long long)batch * H * W * out_channels_total;
+  const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 512;
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)batch, 2};
+    uint32_t b[5] = {64, (uint32_t)p.xw, (uint32_t)p.xh, 1, 2};
+    if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "activations")) return e;
+  }
+  {
+    uint64_t d[4] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)p.taps, 2};
+    uint32_t b[4] = {64, (uint32_t)bn, 1, 2};
+    if (int e = shf_encode_f16_map(&tb, const_cast<void*>(w_h2), 4, d, b, "weights")) return e;
+  }
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return bn == 128 ? launch_stream<128>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64>(ta, tb, p, smem_bytes, grid, st);
+}

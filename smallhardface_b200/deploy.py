@@ -119,13 +119,14 @@ def write_synthetic_deployment(out_dir: str, dilation: bool = True, seed: int = 
     net = build_test_net(dilation, input_hw)
     if dilation:
         net = splice_dim_red(net)
+    tmp = ".tmp%d" % os.getpid()                  # several ranks may race here: each writes its own temp, rename is atomic
     if not os.path.exists(proto):
-        with open(proto + ".tmp", "w") as f:
+        with open(proto + tmp, "w") as f:
             f.write(cp.format_text(net))
-        os.replace(proto + ".tmp", proto)
+        os.replace(proto + tmp, proto)
     if not os.path.exists(model):
         spec = NetSpec(net, TEST)
         params = synthetic_params(spec, seed)
-        cp.write_net_binary(model + ".tmp", params_to_netparameter(spec, params))
-        os.replace(model + ".tmp", model)
+        cp.write_net_binary(model + tmp, params_to_netparameter(spec, params))
+        os.replace(model + tmp, model)
     return proto, model
