@@ -34,6 +34,14 @@ int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void*
                    int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                    float out_scale, int relu, void* stream);
 
+/* shf_conv_igemm + the PoolingLayer MAX 2x2/2 that follows it (pooling_layer.cpp:140-187) in one launch: the pooled
+ * map goes to pool_out_h2 (N, H/2, W/2, pool_channels_total) at pool_channel_offset; out_h2 may be NULL when the
+ * un-pooled blob has no other consumer.  H and W must be even. */
+int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, void* pool_out_h2, int batch,
+                        int H, int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
+                        int out_channel_offset, int pool_channels_total, int pool_channel_offset, float out_scale,
+                        int relu, void* stream);
+
 /* Tuning / test hook: selects the operand-staging strategy of shf_conv_igemm (same results, different smem traffic):
  * 0 = one TMA load per (tap, chunk); 1 = halo tile reused by all taps (default); 2-4 = halo variants under test. */
 int shf_set_conv_impl(int impl);
@@ -66,15 +74,16 @@ int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float* out_chw, i
 /* ---- detection tail -------------------------------------------------------------------------- */
 /* cls_score*/bbox_pred* 1x1 convs + Concat/Reshape + SoftmaxLayer (softmax_layer.cpp:27-60) + the decode half of
  * ProposalLayer.forward (lib/layers/proposal_layer.py:96-173, lib/utils/bbox_transform.py:33-93).
- * feat_h2: host array of num_anchors [dev] pointers (head feature map per anchor, (1,H,W,C) h2).
+ * feat_h2: host array of num_anchors [dev] pointers to ONE image's hi-plane rows (H,W,C) inside an h2 tensor;
+ * feat_plane_stride = elements between its hi and lo planes (N*H*W*C for a batch of N; 0 means H*W*C).
  * w_cls [A][2][C], b_cls [A][2], w_box [A][4][C], b_box [A][4], all fp32 [dev]; base_anchors: host [A][4].
  * Outputs [dev]: prob (2A,H,W) fp32 = cls_prob_reshape_output; delta (4A,H,W) = bbox_pred_output;
  * boxes (H*W*A,4) decoded+clipped, rows ordered (h,w,a); keys (H*W*A) u64 sort keys
  * ((~score_bits)<<32 | row, ~0 for rows below score_thresh / min_size); count = rows >= score_thresh;
  * best_key = smallest key over rows passing min_size. */
-int shf_head_decode(const void* const* feat_h2, int num_anchors, const float* w_cls, const float* b_cls,
-                    const float* w_box, const float* b_box, const float* base_anchors, int H, int W, int C,
-                    int feat_stride, float im_h, float im_w, float min_size, float score_thresh, float* prob,
+int shf_head_decode(const void* const* feat_h2, long long feat_plane_stride, int num_anchors, const float* w_cls,
+                    const float* b_cls, const float* w_box, const float* b_box, const float* base_anchors, int H, int W,
+                    int C, int feat_stride, float im_h, float im_w, float min_size, float score_thresh, float* prob,
                     float* delta, float* boxes, unsigned long long* keys, int* count, unsigned long long* best_key,
                     void* stream);
 

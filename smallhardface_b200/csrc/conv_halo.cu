@@ -26,7 +26,8 @@ int shf_conv_pertap_impl(const void* in_h2, const void* w_h2, const float* bias,
 
 int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
-                         float out_scale, int relu, void* stream);
+                         float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
+                         void* stream);
 
 namespace {
 
@@ -283,6 +284,18 @@ int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 }  // namespace
 
+// Convolution + ReLU + 2x2/2 max pooling in one launch (conv_stream.cu).  out_h2 may be NULL when only the pooled map
+// is consumed downstream (conv1_2, conv2_2, conv3_3 of VGG16); conv4_3 needs both.
+extern "C" int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, void* pool_out_h2,
+                                   int batch, int H, int W, int cin, int cout, int ksize, int dilation,
+                                   int out_channels_total, int out_channel_offset, int pool_channels_total,
+                                   int pool_channel_offset, float out_scale, int relu, void* stream) {
+  SHF_REQUIRE(pool_out_h2 != nullptr, "shf_conv_igemm_pool: pool_out_h2 is NULL");
+  return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
+                              out_channel_offset, out_scale, relu, pool_out_h2, pool_channels_total,
+                              pool_channel_offset, stream);
+}
+
 extern "C" int shf_set_conv_impl(int impl) {
   SHF_REQUIRE(impl >= 0 && impl <= 7, "shf_set_conv_impl: %d", impl);
   g_conv_impl = impl;
@@ -295,7 +308,7 @@ extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* 
                               int out_channel_offset, float out_scale, int relu, void* stream) {
   if (g_conv_impl == 7)
     return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
-                                out_channel_offset, out_scale, relu, stream);
+                                out_channel_offset, out_scale, relu, nullptr, 0, 0, stream);
   if (g_conv_impl == 0)
     return shf_conv_pertap_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                                 out_channel_offset, out_scale, relu, stream);

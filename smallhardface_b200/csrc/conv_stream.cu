@@ -40,8 +40,13 @@ struct StreamParams {
   int ctot, cout_offset, relu;
   float out_scale;
   const float* bias;
-  __half* out;                // h2 destination tensor base (plane 0); plane 1 at + plane_elems
+  __half* out;                // h2 destination tensor base (plane 0); plane 1 at + plane_elems (nullptr: skip)
   long long plane_elems;
+  // fused 2x2/2 max pooling (pooling_layer.cpp:140-187) of the post-ReLU result: every warp of the epilogue holds
+  // a 4x8 pixel patch, so the 2x2 window partners are lanes ^1 (x) and ^8 (y)
+  __half* pool_out;           // nullptr: no pooling
+  long long pool_plane_elems;
+  int pool_ctot, pool_coffset;
 };
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -208,28 +213,58 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive_cnt(acc_empty(set));          // 4 warps -> the set is free again
       }
-      // ---- epilogue for this tile: bias, ReLU, split to hi/lo, NHWC rows straight to global memory ----
+      // ---- epilogue for this tile: bias, ReLU, (2x2 max pool), split to hi/lo, NHWC rows straight to global memory ----
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
-      if (y < p.H && x < p.W) {
-        const int n0 = nt * BN;
-        __half* dst = p.out + ((((size_t)img * p.H + y) * p.W + x) * (size_t)p.ctot + p.cout_offset + n0);
-        const float* bias = p.bias ? p.bias + n0 : nullptr;
+      const bool inside = (y < p.H && x < p.W);
+      const int n0 = nt * BN;
+      const float* bias = p.bias ? p.bias + n0 : nullptr;
+      __half* dst = p.out ? p.out + ((((size_t)img * p.H + y) * p.W + x) * (size_t)p.ctot + p.cout_offset + n0) : nullptr;
+      const bool pool_writer = p.pool_out && inside && !(lane & 9);        // lane bits 0 (x) and 3 (y) clear: window origin
+      __half* pdst = p.pool_out ? p.pool_out + ((((size_t)img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
+                                                    (size_t)p.pool_ctot + p.pool_coffset + n0)
+                                : nullptr;
 #pragma unroll
-        for (int c = 0; c < BN; c += 8) {
+      for (int c = 0; c < BN; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = acc[c + e] * scale + (bias ? __ldg(bias + c + e) : 0.f);
+          if (p.relu) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (dst && inside) {
           uint32_t hi_pk[4], lo_pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float v0 = acc[c + 2 * e] * scale + (bias ? __ldg(bias + c + 2 * e) : 0.f);
-            float v1 = acc[c + 2 * e + 1] * scale + (bias ? __ldg(bias + c + 2 * e + 1) : 0.f);
-            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             __half h0, l0, h1, l1;
-            split_h2(v0, h0, l0);
-            split_h2(v1, h1, l1);
+            split_h2(v[2 * e], h0, l0);
+            split_h2(v[2 * e + 1], h1, l1);
             hi_pk[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             lo_pk[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
           *reinterpret_cast<uint4*>(dst + c) = make_uint4(hi_pk[0], hi_pk[1], hi_pk[2], hi_pk[3]);
           *reinterpret_cast<uint4*>(dst + p.plane_elems + c) = make_uint4(lo_pk[0], lo_pk[1], lo_pk[2], lo_pk[3]);
+        }
+        if (p.pool_out) {                                   // warp-uniform branch: all lanes take part in the shuffles
+          uint32_t hi_pk[4], lo_pk[4];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float q = inside ? v[e] : -3.402823466e38f;
+            q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
+            q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
+            v[e] = q;
+          }
+          if (pool_writer) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __half h0, l0, h1, l1;
+              split_h2(v[2 * e], h0, l0);
+              split_h2(v[2 * e + 1], h1, l1);
+              hi_pk[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              lo_pk[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4*>(pdst + c) = make_uint4(hi_pk[0], hi_pk[1], hi_pk[2], hi_pk[3]);
+            *reinterpret_cast<uint4*>(pdst + p.pool_plane_elems + c) = make_uint4(lo_pk[0], lo_pk[1], lo_pk[2], lo_pk[3]);
+          }
         }
       }
     }
@@ -270,12 +305,18 @@ int sm_count() {
 
 int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
-                         float out_scale, int relu, void* stream) {
+                         float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
+                         void* stream) {
+  SHF_REQUIRE(out_h2 != nullptr || pool_out_h2 != nullptr, "shf_conv_igemm: no destination");
+  if (pool_out_h2)
+    SHF_REQUIRE(H % 2 == 0 && W % 2 == 0 && pool_channel_offset % 8 == 0 && pool_channels_total % 8 == 0 &&
+                    pool_channel_offset + cout <= pool_channels_total,
+                "shf_conv_igemm_pool: fused pooling needs even H, W (got %dx%d) and an 8-aligned channel window", H, W);
   SHF_REQUIRE(ksize == 3 || ksize == 1, "shf_conv_igemm: kernel size %d (only 3x3 and 1x1 are on the hot path)", ksize);
   SHF_REQUIRE(cin % 64 == 0 && cin >= 64, "shf_conv_igemm: Cin=%d must be a multiple of 64", cin);
   SHF_REQUIRE(cout % 64 == 0 && cout >= 64, "shf_conv_igemm: Cout=%d must be a multiple of 64", cout);
-  SHF_REQUIRE(out_channel_offset % 8 == 0 && out_channel_offset + cout <= out_channels_total &&
-                  out_channels_total % 8 == 0,
+  SHF_REQUIRE(out_h2 == nullptr || (out_channel_offset % 8 == 0 && out_channel_offset + cout <= out_channels_total &&
+                                     out_channels_total % 8 == 0),
               "shf_conv_igemm: bad destination channel window [%d,%d) of %d", out_channel_offset,
               out_channel_offset + cout, out_channels_total);
   SHF_REQUIRE(batch >= 1 && H >= 1 && W >= 1 && dilation >= 1 && dilation <= 4, "shf_conv_igemm: bad geometry");
@@ -311,6 +352,10 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.bias = bias;
   p.out = reinterpret_cast<__half*>(out_h2);
   p.plane_elems = (long long)batch * H * W * out_channels_total;
+  p.pool_out = reinterpret_cast<__half*>(pool_out_h2);
+  p.pool_plane_elems = (long long)batch * (H / 2) * (W / 2) * pool_channels_total;
+  p.pool_ctot = pool_channels_total;
+  p.pool_coffset = pool_channel_offset;
   const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 512;
 
   CUtensorMap ta, tb;

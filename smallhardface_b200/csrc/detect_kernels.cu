@@ -26,6 +26,7 @@ struct HeadParams {
   const float* bb;                   // [A][4]
   float anchors[kMaxAnchors][4];     // base anchors (x1,y1,x2,y2), generate_anchors.py
   int A, H, W, C;
+  long long plane_stride;            // elements between the hi and lo planes (= N*H*W*C of the batched tensor)
   int feat_stride;
   float im_h, im_w;                  // unpadded level size (im_info[0:2])
   float min_size;                    // ANCHOR_MIN_SIZE * im_info[2]
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(128) head_decode_kernel(const HeadParams p, fl
   __syncthreads();
   const int hw = p.H * p.W;
   const int n = hw * A;
-  const size_t plane = (size_t)hw * C;
+  const size_t plane = (size_t)p.plane_stride;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // anchor row index, (h, w, a) order
   unsigned long long key = ~0ull, bkey = ~0ull;
   bool cand = false;
@@ -394,9 +395,9 @@ __global__ void bbox_overlaps_kernel(const double* __restrict__ boxes, const dou
 // =================================================================================================
 // C ABI (declared in include/shf_b200.h)
 // =================================================================================================
-extern "C" int shf_head_decode(const void* const* feat_h2, int num_anchors, const float* w_cls, const float* b_cls,
-                               const float* w_box, const float* b_box, const float* base_anchors, int H, int W, int C,
-                               int feat_stride, float im_h, float im_w, float min_size, float score_thresh, float* prob,
+extern "C" int shf_head_decode(const void* const* feat_h2, long long feat_plane_stride, int num_anchors,
+                               const float* w_cls, const float* b_cls, const float* w_box, const float* b_box,
+                               const float* base_anchors, int H, int W, int C, int feat_stride, float im_h, float im_w, float min_size, float score_thresh, float* prob,
                                float* delta, float* boxes, unsigned long long* keys, int* count,
                                unsigned long long* best_key, void* stream) {
   SHF_REQUIRE(num_anchors >= 1 && num_anchors <= kMaxAnchors, "shf_head_decode: %d anchors (max %d)", num_anchors,
@@ -409,6 +410,7 @@ extern "C" int shf_head_decode(const void* const* feat_h2, int num_anchors, cons
   }
   p.wc = w_cls; p.bc = b_cls; p.wb = w_box; p.bb = b_box;
   p.A = num_anchors; p.H = H; p.W = W; p.C = C; p.feat_stride = feat_stride;
+  p.plane_stride = feat_plane_stride > 0 ? feat_plane_stride : (long long)H * W * C;
   p.im_h = im_h; p.im_w = im_w; p.min_size = min_size; p.score_thresh = score_thresh;
   cudaStream_t st = (cudaStream_t)stream;
   SHF_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));

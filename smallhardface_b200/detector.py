@@ -78,6 +78,7 @@ class Detector:
                           score_thresh=self.cfg.score_thresh, min_size=self.cfg.anchor_min_size)
         self._means = (C.c_double * 3)(*self.cfg.pixel_means)
         self._bufs = {}
+        self.max_batch_bytes = 40e9          # activation budget used to size per-level batches (180 GB HBM per GPU)
 
     # ------------------------------------------------------------------------------------------
     def upload(self, images: List[np.ndarray]) -> List[torch.Tensor]:
@@ -108,34 +109,53 @@ class Detector:
             self._bufs[key] = b
         return b
 
-    def _level_blob(self, img: torch.Tensor, s: float, flip: bool):
-        h, w = img.shape[0], img.shape[1]
+    def _level_batch(self, imgs: List[torch.Tensor], s: float, flips):
+        """One pyramid level of several same-sized images (and their mirrors) as a single (N,3,HP,WP) batch."""
+        h, w = imgs[0].shape[0], imgs[0].shape[1]
         oh, ow, hp, wp = level_geometry(h, w, s, self.cfg.max_resolution)
-        data = torch.empty((1, 3, hp, wp), dtype=torch.float32, device=self.device)
-        L.call("shf_preprocess_level", _ptr(img), h, w, _ptr(data), oh, ow, hp, wp, float(s), int(flip), self._means,
-               _stream())
-        self.net.launches += 1
+        data = torch.empty((len(imgs) * len(flips), 3, hp, wp), dtype=torch.float32, device=self.device)
+        st = _stream()
+        for j, img in enumerate(imgs):
+            for f, fl in enumerate(flips):
+                L.call("shf_preprocess_level", _ptr(img), h, w, _ptr(data[j * len(flips) + f]), oh, ow, hp, wp, float(s),
+                       int(fl), self._means, st)
+                self.net.launches += 1
         return data, (oh, ow, s)
 
     def detect_device(self, dev_images: List[torch.Tensor]):
         """Runs the whole pipeline for a batch of device-resident images; returns the device buffers
-        (out_dets (B,max,5), out_idx (B,max), out_count (B,), dets (B,cap,5)) without synchronising."""
+        (out_dets (B,max,5), out_idx (B,max), out_count (B,), dets (B,cap,5)) without synchronising.
+
+        Same-sized images are stacked per pyramid level together with their mirrored copies, so the conv stack
+        sees N = images x flips per launch (the small levels would not fill 148 SMs otherwise); the
+        ProposalLayer tail and the per-pass bookkeeping stay per image, in the reference's pass order
+        (scale 0, scale 0 mirrored, scale 1, ... -- ``lib/test.py:141-155``)."""
         cfg = self.cfg
         flips = (False, True) if cfg.flip else (False,)
+        nf = len(flips)
         nscales = len(cfg.scales) if len(cfg.scales) > 1 else 1
-        passes = nscales * len(flips)
+        passes = nscales * nf
         B = len(dev_images)
         b = self._buffers(B, passes)
         b["offs"].zero_()
+        groups = {}
         for i, img in enumerate(dev_images):
-            scales = pyramid_scales(img.shape, cfg)
-            p = 0
-            for s in scales:
-                for fl in flips:
-                    data, info = self._level_blob(img, s, fl)
-                    self.net.forward(data, info, dets=b["dets"][i], pass_offsets=b["offs"][i], pass_idx=p,
-                                     det_cap=b["cap"], flip=fl, det_thresh=cfg.thresh)
-                    p += 1
+            groups.setdefault((img.shape[0], img.shape[1]), []).append(i)
+        for (h, w), idxs in groups.items():
+            scales = pyramid_scales((h, w, 3), cfg)
+            for li, s in enumerate(scales):
+                _, _, hp, wp = level_geometry(h, w, s, cfg.max_resolution)
+                # activations of the widest layer: 64 ch x 4 B per pixel, a few tensors live at once
+                per_image = hp * wp * 64 * 4 * 3 * nf
+                chunk = max(1, min(len(idxs), int(self.max_batch_bytes // max(1, per_image))))
+                for c0 in range(0, len(idxs), chunk):
+                    sub = idxs[c0:c0 + chunk]
+                    data, info = self._level_batch([dev_images[i] for i in sub], s, flips)
+                    self.net.forward_body(data)
+                    for j, i in enumerate(sub):
+                        for f, fl in enumerate(flips):
+                            self.net.run_tail(j * nf + f, info, dets=b["dets"][i], pass_offsets=b["offs"][i],
+                                              pass_idx=li * nf + f, det_cap=b["cap"], flip=fl, det_thresh=cfg.thresh)
         torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])
         method = 1 if cfg.nms_method == "BBOX_VOTE" else 0
         if cfg.nms_method not in ("BBOX_VOTE", "NMS"):

@@ -119,8 +119,12 @@ class GpuNet:
     the device plus ``im_info`` and leaves every materialised blob in ``self.tensors``."""
 
     def __init__(self, spec: NetSpec, params: Dict[str, np.ndarray], device="cuda:0", pre_nms_topn=10000,
-                 score_thresh=0.002, min_size=0.0):
+                 score_thresh=0.002, min_size=0.0, fuse_pool=True):
+        """``fuse_pool``: run Convolution+ReLU+Pooling(MAX 2x2/2) as one launch; the un-pooled conv blob is then
+        only materialised if something else consumes it (pass False to be able to read every blob)."""
         L.load()
+        import os
+        self.fuse_pool = bool(fuse_pool) and not os.environ.get("SHF_MATERIALIZE_ALL")
         self.spec = spec
         self.device = torch.device(device)
         self.cfg = dict(pre_nms_topn=int(pre_nms_topn), score_thresh=float(score_thresh), min_size=float(min_size))
@@ -208,6 +212,15 @@ class GpuNet:
                     packed, k = pack_conv_weights(w)
                     st["w"] = torch.from_numpy(packed).to(dev)
                     st["scale"] = float(2.0 ** (-k))
+                    nxt = i + (2 if relu else 1)
+                    pl = layers[nxt] if nxt < len(layers) else None
+                    if (self.fuse_pool and pl is not None and pl.type == "Pooling" and pl.bottoms == l.tops
+                            and (pl.p["pool"], pl.p["kh"], pl.p["kw"], pl.p["sh"], pl.p["sw"], pl.p["ph"], pl.p["pw"]) == (0, 2, 2, 2, 2, 0, 0)):
+                        st["pool_top"] = pl.tops[0]
+                        st["write_full"] = len(consumers.get(l.tops[0], [])) > 1      # e.g. conv4_3 also feeds conv4_256
+                        self.ops.append(("conv", l, st))
+                        i = nxt + 1
+                        continue
                     self.ops.append(("conv", l, st))
                 i += 2 if relu else 1
                 continue
@@ -314,9 +327,17 @@ class GpuNet:
 
     def forward(self, data: torch.Tensor, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False,
                 det_thresh=0.05):
-        """data: (N,3,H,W) fp32 on the device.  im_info: (h, w, scale) of the unpadded level.
+        """data: (1,3,H,W) fp32 on the device.  im_info: (h, w, scale) of the unpadded level.
         Returns (boxes (topn,5), probs (topn,2), rows (1,) int32) device tensors; when ``dets`` is given the
         pass is also appended to the image-level detection list (see shf_proposal_gather)."""
+        self.forward_body(data)
+        if self.tail is None:
+            return None
+        return self.run_tail(0, im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh)
+
+    def forward_body(self, data: torch.Tensor):
+        """Runs every layer up to the detection tail on a batch (N,3,H,W); blobs stay on the device in
+        ``self.tensors``.  The ProposalLayer is per image (``proposal_layer.py:74-75``): call ``run_tail(n, ...)``."""
         T = self.tensors
         T.clear()
         T["data"] = data
@@ -335,12 +356,26 @@ class GpuNet:
             elif kind == "conv":
                 if x.c_off != 0 or x.c != x.ctot:
                     raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
-                out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"])
+                fused = "pool_top" in s and x.h % 2 == 0 and x.w % 2 == 0
+                out = None
+                if not fused or s["write_full"]:
+                    out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"])
                 if self.profile:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()
-                L.call("shf_conv_igemm", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
-                       s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), st)
+                if fused:
+                    pooled = self._alloc_out(s["pool_top"], x.n, x.h // 2, x.w // 2, s["cout"])
+                    L.call("shf_conv_igemm_pool", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t if out else None),
+                           _ptr(pooled.t), x.n, x.h, x.w, s["cin"], s["cout"], s["k"], s["dil"],
+                           out.ctot if out else s["cout"], out.c_off if out else 0, pooled.ctot, pooled.c_off,
+                           s["scale"], int(s["relu"]), st)
+                else:
+                    L.call("shf_conv_igemm", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
+                           s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), st)
+                    if "pool_top" in s:                      # odd size: pooling could not be fused
+                        pooled = self._alloc_out(s["pool_top"], x.n, (x.h + 1) // 2, (x.w + 1) // 2, s["cout"])
+                        L.call("shf_maxpool2x2", _ptr(out.t), _ptr(pooled.t), x.n, x.h, x.w, s["cout"], st)
+                        self.launches += 1
                 if self.profile:
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()
@@ -355,19 +390,17 @@ class GpuNet:
                 L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
                        s["pad"], out.ctot, out.c_off, st)
             self.launches += 1
-        if self.tail is None:
-            return None
-        return self._run_tail(im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh)
 
-    def _run_tail(self, im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh):
+    def run_tail(self, n_img, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False, det_thresh=0.05):
+        """Detection tail for image ``n_img`` of the last ``forward_body`` batch."""
         t = self.tail
         T = self.tensors
         dev = self.device
         A, Cf = t["A"], t["C"]
         feats = [T[f] for f in t["feats"]]
         f0 = feats[0]
-        if f0.n != 1:
-            raise L.ShfError("the ProposalLayer supports single-image batches only (proposal_layer.py:74-75)")
+        if not (0 <= n_img < f0.n):
+            raise L.ShfError("image index %d outside the batch of %d" % (n_img, f0.n))
         H, W = f0.h, f0.w
         hw, n = H * W, H * W * A
         key = ("tailbuf", n)
@@ -386,7 +419,9 @@ class GpuNet:
                        out_probs=torch.empty((min(topn, n), 2), dtype=torch.float32, device=dev), topn=min(topn, n))
             self._tailbuf = buf
         st = _stream()
-        fp = (C.c_void_p * A)(*[f.t.data_ptr() for f in feats])
+        img_bytes = H * W * Cf * 2
+        fp = (C.c_void_p * A)(*[f.t.data_ptr() + n_img * img_bytes for f in feats])
+        plane_stride = f0.n * H * W * Cf
         anchors = t["anchors"]
         ap = anchors.ctypes.data_as(C.POINTER(C.c_float))
         meta32 = buf["meta"].view(torch.int32)
@@ -395,7 +430,7 @@ class GpuNet:
         best_ptr = C.c_void_p(buf["meta"].data_ptr() + 8)
         im_h, im_w, im_scale = float(im_info[0]), float(im_info[1]), float(im_info[2])
         min_size = float(F32(self.cfg["min_size"]) * F32(im_scale))
-        L.call("shf_head_decode", fp, A, _ptr(t["wc"]), _ptr(t["bc"]), _ptr(t["wb"]), _ptr(t["bb"]), ap, H, W, Cf,
+        L.call("shf_head_decode", fp, plane_stride, A, _ptr(t["wc"]), _ptr(t["bc"]), _ptr(t["wb"]), _ptr(t["bb"]), ap, H, W, Cf,
                t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])), _ptr(buf["prob"]), _ptr(buf["delta"]),
                _ptr(buf["boxes"]), _ptr(buf["keys"]), count_ptr, best_ptr, st)
         L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), n, _ptr(buf["ws"]), buf["ws_bytes"], st)
@@ -414,6 +449,9 @@ class GpuNet:
         if name not in self.tensors:
             if self.tail and name in self._fused_tail_blobs():
                 raise L.ShfError("blob %r is fused into the detection-tail kernel and never materialised" % name)
+            if name in self.spec.blob_names:
+                raise L.ShfError("blob %r is fused into a conv+pool launch and never materialised "
+                                 "(construct GpuNet(fuse_pool=False) or set SHF_MATERIALIZE_ALL=1 to read it)" % name)
             raise KeyError(name)
         t = self.tensors[name]
         return t.to_nchw() if isinstance(t, H2) else t

@@ -24,6 +24,8 @@ SIGNATURES = {
     "shf_device_info": (c_int, [c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_ll)]),
     "shf_conv_igemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_float, c_int, c_void_p]),
+    "shf_conv_igemm_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "shf_set_conv_impl": (c_int, [c_int]),
     "shf_conv1_c3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -33,7 +35,7 @@ SIGNATURES = {
     "shf_nchw_to_h2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_preprocess_level": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
                                      C.POINTER(c_double), c_void_p]),
-    "shf_head_decode": (c_int, [C.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+    "shf_head_decode": (c_int, [C.POINTER(c_void_p), c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 C.POINTER(c_float), c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "shf_sort_keys_workspace": (c_ll, [c_int]),

@@ -121,6 +121,29 @@ def test_conv_igemm_matches_oracle(cin, cout, H, W, k, dil, ctot, coff, relu):
     assert relerr(out2.to_nchw().cpu().numpy(), ref) < 3e-6
 
 
+@pytest.mark.parametrize("cin,cout,H,W,write_full", [(64, 64, 32, 48, 0), (128, 128, 18, 22, 1), (256, 256, 16, 8, 0)])
+def test_conv_relu_pool_fused(cin, cout, H, W, write_full):
+    """Convolution + ReLU + MAX 2x2/2 pooling in one launch vs the three oracle layers."""
+    rng = np.random.RandomState(cin + H)
+    x = h2_roundtrip_np(np.abs(rng.randn(2, cin, H, W) * 20).astype(F32))
+    w = (rng.randn(cout, cin, 3, 3) * np.sqrt(2.0 / (cin * 9))).astype(F32)
+    b = (rng.randn(cout) * 0.5).astype(F32)
+    packed, kexp = pack_conv_weights(w)
+    w_eff = ((packed[0].astype(F32) + packed[1].astype(F32)) * F32(2.0 ** -kexp)).reshape(3, 3, cout, cin).transpose(2, 3, 0, 1)
+    xin = H2.from_nchw(dev(x))
+    full = H2.empty(2, H, W, cout, DEV) if write_full else None
+    pooled = H2(torch.zeros((2, 2, H // 2, W // 2, cout + 64), dtype=torch.float16, device=DEV), 64, cout)
+    L.call("shf_conv_igemm_pool", _ptr(xin.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(full.t if full else None),
+           _ptr(pooled.t), 2, H, W, cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, _stream())
+    ref = OL.relu(OL.conv(x, w_eff, b, pad=(1, 1)))
+    refp = OL.max_pool(ref)
+    got = pooled.to_nchw().cpu().numpy()
+    assert got.shape == refp.shape and relerr(got, refp) < 3e-6
+    assert torch.all(pooled.t[..., :64] == 0)
+    if full is not None:
+        assert relerr(full.to_nchw().cpu().numpy(), ref) < 3e-6
+
+
 def test_conv_igemm_batch2():
     rng = np.random.RandomState(5)
     x = h2_roundtrip_np(np.abs(rng.randn(2, 64, 18, 20) * 10).astype(F32))
@@ -196,7 +219,7 @@ def _run_tail(feat_nchw, wc, bc, wb, bb, im_info, topn=10000, score_thresh=0.002
     ob = torch.empty((min(topn, n), 5), dtype=torch.float32, device=DEV)
     op = torch.empty((min(topn, n), 2), dtype=torch.float32, device=DEV)
     cptr, rptr, bptr = (C.c_void_p(meta.data_ptr() + o) for o in (0, 4, 8))
-    L.call("shf_head_decode", fp, A, _ptr(dev(wc)), _ptr(dev(bc)), _ptr(dev(wb)), _ptr(dev(bb)),
+    L.call("shf_head_decode", fp, 0, A, _ptr(dev(wc)), _ptr(dev(bc)), _ptr(dev(wb)), _ptr(dev(bb)),
            anchors.ctypes.data_as(C.POINTER(C.c_float)), H, W, Cc, 8, float(im_info[0]), float(im_info[1]), 0.0,
            float(F32(score_thresh)), _ptr(prob), _ptr(delta), _ptr(boxes), _ptr(keys), cptr, bptr, _stream())
     L.call("shf_sort_keys", _ptr(keys), _ptr(skeys), n, _ptr(ws), ws_bytes, _stream())

@@ -52,7 +52,7 @@ def nets(request, tmp_path_factory):
     proto, model = deploy.write_synthetic_deployment(str(d), dilation=request.param)
     spec = NetSpec(cp.read_net_text(proto))
     params = load_weights(spec, cp.read_net_binary(model))
-    return request.param, proto, model, GpuNet(spec, params, "cuda:0"), OracleNet(proto, model, engine="sgemm", fast=True)
+    return request.param, proto, model, GpuNet(spec, params, "cuda:0", fuse_pool=False), OracleNet(proto, model, engine="sgemm", fast=True)
 
 
 def test_net_forward_224_blobs_and_outputs(nets):
@@ -85,6 +85,42 @@ def test_net_forward_224_blobs_and_outputs(nets):
     ws, wb = match_rows(gb[:, 1:], gp[:, 1], ref["boxes"][:, 1:], ref["cls_prob"][:, 1])
     print("rows %d (ref %d): worst score err %.2e, worst box err %.2e px" % (R, len(ref["boxes"]), ws, wb))
     assert ws < SCORE_TOL and wb < BOX_TOL
+
+
+def test_fused_pool_plan_matches_unfused(nets):
+    """The default plan (conv+ReLU+pool in one launch, un-pooled blobs not materialised) gives the same outputs."""
+    dil, proto, model, gnet, onet = nets
+    fused = GpuNet(gnet.spec, load_weights(gnet.spec, cp.read_net_binary(model)), "cuda:0")
+    assert fused.fuse_pool and sum(1 for k, l, s in fused.ops if k == "conv" and "pool_top" in s) == 4
+    im = parity_image()
+    data = np.ascontiguousarray((im.astype(F32) - np.array([[[102.9801, 115.9465, 122.7717]]])).astype(F32).transpose(2, 0, 1)[None])
+    info = np.array([[224, 224, 1.0]], F32)
+    onet.forward(data=data, im_info=info)
+    boxes, probs, rows = fused.forward(torch.from_numpy(data).to(DEV), info[0])
+    for nm in ["pool1", "pool2", "pool3", "conv4_3", "pool4", "conv5_3"]:
+        got, want = fused.blob_nchw(nm).cpu().numpy(), onet.blobs[nm]
+        assert got.shape == want.shape and np.abs(got - want).max() / np.abs(want).max() < 2e-5, nm
+    with pytest.raises(Exception, match="fused"):
+        fused.blob_nchw("conv1_2")
+    assert np.abs(fused.blob_nchw("cls_prob_reshape_output").cpu().numpy() - onet.blobs["cls_prob_reshape_output"]).max() < SCORE_TOL
+
+
+def test_batched_body_equals_single_image(nets):
+    """N = images x flips through one launch per layer gives the per-image results bit for bit."""
+    dil, proto, model, gnet, onet = nets
+    rng = np.random.RandomState(0)
+    data = (rng.rand(3, 3, 64, 96) * 255 - 110).astype(F32)
+    gnet.forward_body(torch.from_numpy(data).to(DEV))
+    batched = gnet.blob_nchw("conv4_fuse_final").cpu().numpy()
+    outs = []
+    for n in range(3):
+        outs.append([t.clone() for t in gnet.run_tail(n, (60, 90, 1.0))])
+    for n in range(3):
+        gnet.forward_body(torch.from_numpy(data[n:n + 1]).to(DEV))
+        assert np.array_equal(gnet.blob_nchw("conv4_fuse_final").cpu().numpy()[0], batched[n])
+        b, p, r = gnet.run_tail(0, (60, 90, 1.0))
+        R = int(r.item())
+        assert R == int(outs[n][2].item()) and torch.equal(b[:R], outs[n][0][:R]) and torch.equal(p[:R], outs[n][1][:R])
 
 
 @pytest.mark.parametrize("method", ["BBOX_VOTE", "NMS"])
