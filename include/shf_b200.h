@@ -87,6 +87,24 @@ int shf_head_decode(const void* const* feat_h2, long long feat_plane_stride, int
                     float* delta, float* boxes, unsigned long long* keys, int* count, unsigned long long* best_key,
                     void* stream);
 
+/* The same for all images of one pyramid-level batch in ONE launch (the pyramid driver's form).  feat_h2 point at
+ * image 0; image i starts feat_image_stride elements later.  Outputs are [image][...] slices of the single-image
+ * layout; keys are tagged [image:5][~score:32][row:27] so one shf_sort_keys over num_images*n keys sorts every image. */
+int shf_head_decode_batched(const void* const* feat_h2, long long feat_plane_stride, long long feat_image_stride,
+                            int num_images, int num_anchors, const float* w_cls, const float* b_cls, const float* w_box,
+                            const float* b_box, const float* base_anchors, int H, int W, int C, int feat_stride,
+                            float im_h, float im_w, float min_size, float score_thresh, float* prob, float* delta,
+                            float* boxes, unsigned long long* keys, int* count, unsigned long long* best_key,
+                            void* stream);
+
+/* lib/test.py:52-66,141-167 for one level of a batch: per image, the plain and the mirrored pass (slots 2j, 2j+1 of the
+ * batched decode) are un-mirrored, divided by im_scale, thresholded (fg > det_thresh) and appended in that order to
+ * dets[image_base + j] at pass_offsets[image][pass_base], updating pass_offsets[image][pass_base + 1 (+2)]. */
+int shf_gather_dets_batched(const unsigned long long* sorted_keys, const int* count, const unsigned long long* best_key,
+                            const float* prob, const float* boxes, int num_anchors, int hw, int topn, int num_images,
+                            int passes_per_image, float* dets, int* pass_offsets, int image_base, int passes_total,
+                            int pass_base, int det_cap, float level_w, float im_scale, float det_thresh, void* stream);
+
 /* `max_score.argsort()[::-1]` (proposal_layer.py:181) as an ascending radix sort of the keys above
  * (ties: lower row first). */
 long long shf_sort_keys_workspace(int n);

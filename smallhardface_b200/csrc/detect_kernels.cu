@@ -27,6 +27,8 @@ struct HeadParams {
   float anchors[kMaxAnchors][4];     // base anchors (x1,y1,x2,y2), generate_anchors.py
   int A, H, W, C;
   long long plane_stride;            // elements between the hi and lo planes (= N*H*W*C of the batched tensor)
+  long long image_stride;            // elements between consecutive images of the batch (H*W*C); batched launches only
+  int batched;                       // 1: blockIdx.y = image, outputs strided per image, keys carry the image tag
   int feat_stride;
   float im_h, im_w;                  // unpadded level size (im_info[0:2])
   float min_size;                    // ANCHOR_MIN_SIZE * im_info[2]
@@ -36,6 +38,15 @@ struct HeadParams {
 SHF_DEVICE unsigned long long make_key(float score, unsigned idx) {
   return ((unsigned long long)(~__float_as_uint(score)) << 32) | idx;     // ascending key = descending score, then index
 }
+// Batched variant: [image : 5][~score bits : 32][row : 27] -- one device-wide sort leaves every image's rows
+// contiguous (each image contributes exactly n keys, sentinels included) and ordered like make_key.
+constexpr int kRowBits = 27;
+SHF_DEVICE unsigned long long make_key_img(unsigned img, float score, unsigned idx) {
+  return ((unsigned long long)img << 59) | ((unsigned long long)(~__float_as_uint(score)) << kRowBits) | idx;
+}
+SHF_DEVICE unsigned long long sentinel_img(unsigned img) { return ((unsigned long long)img << 59) | ((1ull << 59) - 1); }
+SHF_DEVICE float key_img_score(unsigned long long k) { return __uint_as_float(~(unsigned)((k >> kRowBits) & 0xffffffffu)); }
+SHF_DEVICE unsigned key_img_row(unsigned long long k) { return (unsigned)(k & ((1u << kRowBits) - 1)); }
 
 __global__ void __launch_bounds__(128) head_decode_kernel(const HeadParams p, float* __restrict__ prob,
                                                           float* __restrict__ delta, float* __restrict__ boxes,
@@ -57,12 +68,21 @@ __global__ void __launch_bounds__(128) head_decode_kernel(const HeadParams p, fl
   const int n = hw * A;
   const size_t plane = (size_t)p.plane_stride;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // anchor row index, (h, w, a) order
-  unsigned long long key = ~0ull, bkey = ~0ull;
+  const unsigned img = p.batched ? blockIdx.y : 0u;
+  if (p.batched) {                                          // per-image output slices
+    prob += (size_t)img * 2 * A * hw;
+    delta += (size_t)img * 4 * A * hw;
+    boxes += (size_t)img * n * 4;
+    keys += (size_t)img * n;
+    count += img;
+    best_key += img;
+  }
+  unsigned long long key = p.batched ? sentinel_img(img) : ~0ull, bkey = ~0ull;
   bool cand = false;
   if (i < n) {
     const int a = i % A, pix = i / A;
     const int x = pix % p.W, y = pix / p.W;
-    const __half* fh = p.feat[a] + (size_t)pix * C;
+    const __half* fh = p.feat[a] + (size_t)img * p.image_stride + (size_t)pix * C;
     const __half* fl = fh + plane;
     const float* w = wsm + (size_t)a * 6 * C;
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -111,7 +131,7 @@ __global__ void __launch_bounds__(128) head_decode_kernel(const HeadParams p, fl
     // _filter_boxes (proposal_layer.py:231-236) then score threshold (:183-190)
     const float bw = __fadd_rn(__fsub_rn(x2, x1), 1.0f), bh = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
     if (bw >= p.min_size && bh >= p.min_size) {
-      bkey = make_key(pfg, (unsigned)i);
+      bkey = p.batched ? make_key_img(img, pfg, (unsigned)i) : make_key(pfg, (unsigned)i);
       if (pfg >= p.score_thresh) { key = bkey; cand = true; }
     }
     keys[i] = key;
@@ -187,6 +207,78 @@ __global__ void __launch_bounds__(256) proposal_gather_kernel(const GatherParams
       float x1 = b.x, x2 = b.z;
       if (g.flip) { x1 = __fsub_rn(g.level_w, b.z); x2 = __fsub_rn(g.level_w, b.x); }   // boxes[:, [1,3]] = w - boxes[:, [3,1]]
       float* d = g.dets + (size_t)(base + j) * 5;
+      d[0] = __fdiv_rn(x1, g.im_scale); d[1] = __fdiv_rn(b.y, g.im_scale);
+      d[2] = __fdiv_rn(x2, g.im_scale); d[3] = __fdiv_rn(b.w, g.im_scale);
+      d[4] = pfg;
+    }
+  }
+}
+
+// Batched form used by the pyramid driver: one launch per level for all images of the batch and both mirror
+// passes.  blockIdx.y = image; the two passes of an image (plain, mirrored) are appended back to back in the
+// reference's order, which makes the pass-offset chain of lib/test.py:141-158 a per-image serial dependency that
+// one block row resolves locally.
+struct GatherBatchParams {
+  const unsigned long long* sorted;  // [slots][n] image-tagged keys, each slot's rows contiguous and ordered
+  const int* count;                  // [slots]
+  const unsigned long long* best_key;// [slots]
+  const float* prob;                 // [slots][2A][hw]
+  const float* boxes;                // [slots][n][4]
+  int A, hw, n, topn, nf;            // nf = passes per image at this level (1 or 2: plain, mirrored)
+  float* dets;                       // [images][det_cap][5]
+  int* pass_offsets;                 // [images][passes_total + 1]
+  int image_base, passes_total, pass_base, det_cap;
+  float level_w, im_scale, det_thresh;
+};
+
+__global__ void __launch_bounds__(256) gather_dets_batched_kernel(const GatherBatchParams g) {
+  const int j = blockIdx.y;                              // image within the level batch
+  const int image = g.image_base + j;
+  int* offs = g.pass_offsets + (size_t)image * (g.passes_total + 1);
+  float* dets = g.dets + (size_t)image * g.det_cap * 5;
+  __shared__ int s_R[2], s_keep[2], s_base[2];
+  if (threadIdx.x < g.nf) {
+    const int f = threadIdx.x, slot = j * g.nf + f;
+    const int cnt = g.count[slot];
+    const bool any = g.best_key[slot] != ~0ull;
+    const int R = cnt > 0 ? min(cnt, g.topn) : (any ? 1 : 0);
+    const unsigned long long* keys = g.sorted + (size_t)slot * g.n;
+    int lo = 0, hi = R;                                  // rows with score > det_thresh are a prefix
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const unsigned long long k = cnt > 0 ? keys[mid] : g.best_key[slot];
+      if (key_img_score(k) > g.det_thresh) lo = mid + 1; else hi = mid;
+    }
+    s_R[f] = R;
+    s_keep[f] = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int base = offs[g.pass_base];
+    for (int f = 0; f < g.nf; ++f) {
+      s_base[f] = base;
+      base = min(base + s_keep[f], g.det_cap);
+      if (blockIdx.x == 0) offs[g.pass_base + f + 1] = base;
+    }
+  }
+  __syncthreads();
+  for (int f = 0; f < g.nf; ++f) {
+    const int slot = j * g.nf + f;
+    const int keep = s_keep[f], base = s_base[f];
+    const int cnt = g.count[slot];
+    const unsigned long long* keys = g.sorted + (size_t)slot * g.n;
+    const float* prob = g.prob + (size_t)slot * 2 * g.A * g.hw;
+    const float4* boxes = reinterpret_cast<const float4*>(g.boxes) + (size_t)slot * g.n;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < keep; r += gridDim.x * blockDim.x) {
+      if (base + r >= g.det_cap) break;
+      const unsigned long long k = cnt > 0 ? keys[r] : g.best_key[slot];
+      const unsigned i = key_img_row(k);
+      const int a = i % g.A, pix = i / g.A;
+      const float4 b = boxes[i];
+      const float pfg = prob[(size_t)(g.A + a) * g.hw + pix];
+      float x1 = b.x, x2 = b.z;
+      if (f == 1) { x1 = __fsub_rn(g.level_w, b.z); x2 = __fsub_rn(g.level_w, b.x); }      // un-mirror, lib/test.py:52-54
+      float* d = dets + (size_t)(base + r) * 5;
       d[0] = __fdiv_rn(x1, g.im_scale); d[1] = __fdiv_rn(b.y, g.im_scale);
       d[2] = __fdiv_rn(x2, g.im_scale); d[3] = __fdiv_rn(b.w, g.im_scale);
       d[4] = pfg;
@@ -411,6 +503,7 @@ extern "C" int shf_head_decode(const void* const* feat_h2, long long feat_plane_
   p.wc = w_cls; p.bc = b_cls; p.wb = w_box; p.bb = b_box;
   p.A = num_anchors; p.H = H; p.W = W; p.C = C; p.feat_stride = feat_stride;
   p.plane_stride = feat_plane_stride > 0 ? feat_plane_stride : (long long)H * W * C;
+  p.image_stride = 0; p.batched = 0;
   p.im_h = im_h; p.im_w = im_w; p.min_size = min_size; p.score_thresh = score_thresh;
   cudaStream_t st = (cudaStream_t)stream;
   SHF_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
@@ -423,6 +516,57 @@ extern "C" int shf_head_decode(const void* const* feat_h2, long long feat_plane_
     smem_set = smem;
   }
   head_decode_kernel<<<(n + 127) / 128, 128, smem, st>>>(p, prob, delta, boxes, keys, count, best_key);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+// Batched head decode for the pyramid driver: `num_images` images of one level batch in a single launch.
+// Outputs are per image ([img][...]) and the sort keys carry the image index in their top bits (see make_key_img),
+// so a single shf_sort_keys over num_images * n keys orders every image's rows.
+extern "C" int shf_head_decode_batched(const void* const* feat_h2, long long feat_plane_stride, long long feat_image_stride,
+                                       int num_images, int num_anchors, const float* w_cls, const float* b_cls,
+                                       const float* w_box, const float* b_box, const float* base_anchors, int H, int W,
+                                       int C, int feat_stride, float im_h, float im_w, float min_size, float score_thresh,
+                                       float* prob, float* delta, float* boxes, unsigned long long* keys, int* count,
+                                       unsigned long long* best_key, void* stream) {
+  SHF_REQUIRE(num_anchors >= 1 && num_anchors <= kMaxAnchors, "shf_head_decode_batched: %d anchors (max %d)", num_anchors,
+              kMaxAnchors);
+  SHF_REQUIRE(num_images >= 1 && num_images <= 32, "shf_head_decode_batched: %d images (1..32 per launch)", num_images);
+  SHF_REQUIRE(C % 8 == 0 && (long long)H * W * num_anchors < (1ll << kRowBits), "shf_head_decode_batched: bad geometry");
+  HeadParams p;
+  for (int a = 0; a < num_anchors; ++a) {
+    p.feat[a] = (const __half*)feat_h2[a];
+    for (int k = 0; k < 4; ++k) p.anchors[a][k] = base_anchors[a * 4 + k];
+  }
+  p.wc = w_cls; p.bc = b_cls; p.wb = w_box; p.bb = b_box;
+  p.A = num_anchors; p.H = H; p.W = W; p.C = C; p.feat_stride = feat_stride;
+  p.plane_stride = feat_plane_stride; p.image_stride = feat_image_stride; p.batched = 1;
+  p.im_h = im_h; p.im_w = im_w; p.min_size = min_size; p.score_thresh = score_thresh;
+  cudaStream_t st = (cudaStream_t)stream;
+  SHF_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int) * num_images, st));
+  SHF_CUDA_CHECK(cudaMemsetAsync(best_key, 0xff, sizeof(unsigned long long) * num_images, st));
+  const int n = H * W * num_anchors;
+  const size_t smem = (size_t)num_anchors * 6 * (C + 1) * sizeof(float);
+  SHF_REQUIRE(smem <= 48 * 1024, "shf_head_decode_batched: head weights do not fit the default shared memory");
+  dim3 grid((n + 127) / 128, num_images);
+  head_decode_kernel<<<grid, 128, smem, st>>>(p, prob, delta, boxes, keys, count, best_key);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_gather_dets_batched(const unsigned long long* sorted_keys, const int* count,
+                                       const unsigned long long* best_key, const float* prob, const float* boxes,
+                                       int num_anchors, int hw, int topn, int num_images, int passes_per_image,
+                                       float* dets, int* pass_offsets, int image_base, int passes_total, int pass_base,
+                                       int det_cap, float level_w, float im_scale, float det_thresh, void* stream) {
+  SHF_REQUIRE(passes_per_image == 1 || passes_per_image == 2, "shf_gather_dets_batched: %d passes per image", passes_per_image);
+  GatherBatchParams g;
+  g.sorted = sorted_keys; g.count = count; g.best_key = best_key; g.prob = prob; g.boxes = boxes;
+  g.A = num_anchors; g.hw = hw; g.n = hw * num_anchors; g.topn = topn; g.nf = passes_per_image;
+  g.dets = dets; g.pass_offsets = pass_offsets; g.image_base = image_base; g.passes_total = passes_total;
+  g.pass_base = pass_base; g.det_cap = det_cap; g.level_w = level_w; g.im_scale = im_scale; g.det_thresh = det_thresh;
+  dim3 grid(8, num_images);
+  gather_dets_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
   SHF_LAUNCH_CHECK();
   return 0;
 }

@@ -32,52 +32,81 @@ template <int COUT>
 __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                          const float* __restrict__ bias, __half* __restrict__ out,
                                                          int N, int H, int W, int relu) {
-  __shared__ float ws[27][COUT];     // [c*9 + r*3 + s][o]
+  // Register-blocked: one thread = two horizontally adjacent output pixels x all COUT channels, 16 channels at a
+  // time; weights come from shared memory as float4 (one LDS.128 feeds 8 FMAs), inputs through the read-only path.
+  __shared__ float4 ws[27][COUT / 4];     // [c*9 + r*3 + s][o/4]
   __shared__ float bs[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
     const int o = i / 27, k = i % 27;            // weights arrive OIHW: w[o][c][r][s]
-    ws[k][o] = w[i];
+    reinterpret_cast<float*>(&ws[k][0])[o] = w[i];
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const long long npix = (long long)N * H * W;
-  const size_t plane = (size_t)npix * COUT;
-  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
-       pix += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(pix % W);
-    const int y = (int)((pix / W) % H);
-    const int n = (int)(pix / ((long long)W * H));
-    float v[27];
+  const int WP = (W + 1) / 2;                    // pixel pairs per row
+  const long long npairs = (long long)N * H * WP;
+  const size_t plane = (size_t)N * H * W * COUT;
+  for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs;
+       pr += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(pr % WP);
+    const int y = (int)((pr / WP) % H);
+    const int n = (int)(pr / ((long long)WP * H));
+    const int x = xp * 2;
+    const bool has2 = (x + 1 < W);
+    float v[3][3][4];                            // [c][r][columns x-1 .. x+2]
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r) {
+        const int iy = y + r - 1;
+        const float* row = in + (((size_t)n * 3 + c) * H + iy) * W;
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int iy = y + r - 1, ix = x + s - 1;
-          v[c * 9 + r * 3 + s] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                                     ? __ldg(in + (((size_t)n * 3 + c) * H + iy) * W + ix) : 0.f;
+        for (int q = 0; q < 4; ++q) {
+          const int ix = x + q - 1;
+          v[c][r][q] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(row + ix) : 0.f;
         }
-    __half* ohi = out + (size_t)pix * COUT;
+      }
+    const size_t pix = ((size_t)n * H + y) * W + x;
+    __half* ohi = out + pix * COUT;
     __half* olo = ohi + plane;
 #pragma unroll 1
-    for (int o0 = 0; o0 < COUT; o0 += 8) {
-      float acc[8];
+    for (int o0 = 0; o0 < COUT; o0 += 16) {
+      float a0[16], a1[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 16; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
 #pragma unroll
-      for (int k = 0; k < 27; ++k)
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[k], ws[k][o0 + j], acc[j]);
-      __half hi[8], lo[8];
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = acc[j] + bs[o0 + j];
-        if (relu) t = fmaxf(t, 0.f);
-        split_h2(t, hi[j], lo[j]);
+          for (int t = 0; t < 3; ++t) {
+            const float p0 = v[c][r][t], p1 = v[c][r][t + 1];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 wv = ws[c * 9 + r * 3 + t][o0 / 4 + g];
+              a0[4 * g + 0] = fmaf(p0, wv.x, a0[4 * g + 0]); a1[4 * g + 0] = fmaf(p1, wv.x, a1[4 * g + 0]);
+              a0[4 * g + 1] = fmaf(p0, wv.y, a0[4 * g + 1]); a1[4 * g + 1] = fmaf(p1, wv.y, a1[4 * g + 1]);
+              a0[4 * g + 2] = fmaf(p0, wv.z, a0[4 * g + 2]); a1[4 * g + 2] = fmaf(p1, wv.z, a1[4 * g + 2]);
+              a0[4 * g + 3] = fmaf(p0, wv.w, a0[4 * g + 3]); a1[4 * g + 3] = fmaf(p1, wv.w, a1[4 * g + 3]);
+            }
+          }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __half hi[8], lo[8], hi2[8], lo2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t0 = a0[h * 8 + j] + bs[o0 + h * 8 + j];
+          float t1 = a1[h * 8 + j] + bs[o0 + h * 8 + j];
+          if (relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+          split_h2(t0, hi[j], lo[j]);
+          split_h2(t1, hi2[j], lo2[j]);
+        }
+        *reinterpret_cast<uint4*>(ohi + o0 + h * 8) = pack8(hi);
+        *reinterpret_cast<uint4*>(olo + o0 + h * 8) = pack8(lo);
+        if (has2) {
+          *reinterpret_cast<uint4*>(ohi + COUT + o0 + h * 8) = pack8(hi2);
+          *reinterpret_cast<uint4*>(olo + COUT + o0 + h * 8) = pack8(lo2);
+        }
       }
-      *reinterpret_cast<uint4*>(ohi + o0) = pack8(hi);
-      *reinterpret_cast<uint4*>(olo + o0) = pack8(lo);
     }
   }
 }
@@ -163,6 +192,56 @@ __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           acc[j] += join_h2(h[j], l[j]) * __ldg(w + ((size_t)(c8 * 8 + j) * K + ky) * K + kx);
+      }
+    }
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_h2(acc[j], hi[j], lo[j]);
+    const size_t o = (((size_t)n * HO + oy) * WO + ox) * CT + c_off + (size_t)c8 * 8;
+    *reinterpret_cast<uint4*>(out + o) = pack8(hi);
+    *reinterpret_cast<uint4*>(out + out_plane + o) = pack8(lo);
+  }
+}
+
+// Fast path for the net's own upsampler (k = 4, stride 2, pad 1): every output pixel has exactly 2 x 2 taps,
+// ky = ((oy+1)&1) + {0,2} reading input rows (oy+1-ky)/2.  Per-channel 4x4 filters sit in shared memory; the tap
+// loops are fully unrolled so the 8 operand loads of a thread are all in flight together.  Accumulation order
+// (ky ascending, then kx ascending) is the same as the generic kernel / col2im.
+__global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
+                                                               __half* __restrict__ out, int N, int H, int W, int C,
+                                                               int CT, int c_off) {
+  extern __shared__ float wsm[];                 // [C][16]
+  for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int HO = 2 * H, WO = 2 * W, cv = C / 8;
+  const long long total = (long long)N * HO * WO * cv;
+  const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * CT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const int ox = (int)((i / cv) % WO);
+    const int oy = (int)((i / ((long long)cv * WO)) % HO);
+    const int n = (int)(i / ((long long)cv * WO * HO));
+    const int ky0 = (oy + 1) & 1, kx0 = (ox + 1) & 1;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ky0 + 2 * a;
+      const int iy = (oy + 1 - ky) >> 1;          // exact: oy+1-ky is even
+      if (oy + 1 - ky < 0 || iy >= H) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kx = kx0 + 2 * b;
+        const int ix = (ox + 1 - kx) >> 1;
+        if (ox + 1 - kx < 0 || ix >= W) continue;
+        const size_t off = (((size_t)n * H + iy) * W + ix) * C + (size_t)c8 * 8;
+        __half h[8], l[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(in + off)), h);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(in + in_plane + off)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += join_h2(h[j], l[j]) * wsm[(c8 * 8 + j) * 16 + ky * 4 + kx];
       }
     }
     __half hi[8], lo[8];
@@ -318,7 +397,7 @@ int grid_for(long long total, int block) {
 extern "C" int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch,
                             int H, int W, int cout, int relu, void* stream) {
   SHF_REQUIRE(cout == 64, "shf_conv1_c3: Cout=%d (the deploy nets' conv1_1 has 64)", cout);
-  const long long npix = (long long)batch * H * W;
+  const long long npix = (long long)batch * H * ((W + 1) / 2);      // one thread per pixel pair
   conv3x3_c3_kernel<64><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(in_nchw, w_oihw, bias, (__half*)out_h2,
                                                                                batch, H, W, relu);
   SHF_LAUNCH_CHECK();
@@ -342,6 +421,12 @@ extern "C" int shf_deconv_depthwise(const void* in_h2, const float* w, void* out
               "shf_deconv_depthwise: channel counts must be multiples of 8");
   const int HO = stride * (H - 1) + ksize - 2 * pad, WO = stride * (W - 1) + ksize - 2 * pad;   // deconv_layer.cpp:8-28
   const long long total = (long long)batch * HO * WO * (C / 8);
+  if (ksize == 4 && stride == 2 && pad == 1 && C * 16 * sizeof(float) <= 48 * 1024) {
+    deconv_k4s2p1_h2_kernel<<<grid_for(total, 256), 256, C * 16 * sizeof(float), (cudaStream_t)stream>>>(
+        (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, out_channels_total, out_channel_offset);
+    SHF_LAUNCH_CHECK();
+    return 0;
+  }
   deconv_dw_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, ksize, stride, pad, HO, WO, out_channels_total,
       out_channel_offset);

@@ -141,21 +141,26 @@ class Detector:
         groups = {}
         for i, img in enumerate(dev_images):
             groups.setdefault((img.shape[0], img.shape[1]), []).append(i)
+        # buffer slot k holds image order[k]: same-sized images occupy consecutive slots, which is what the batched
+        # tail kernels index by; download() undoes the permutation
+        order = [i for idxs in groups.values() for i in idxs]
+        b["order"] = order
+        slot_of = {img_i: k for k, img_i in enumerate(order)}
+        dev_images = [dev_images[i] for i in order]
+        groups = {hw: [slot_of[i] for i in idxs] for hw, idxs in groups.items()}
         for (h, w), idxs in groups.items():
             scales = pyramid_scales((h, w, 3), cfg)
             for li, s in enumerate(scales):
                 _, _, hp, wp = level_geometry(h, w, s, cfg.max_resolution)
                 # activations of the widest layer: 64 ch x 4 B per pixel, a few tensors live at once
                 per_image = hp * wp * 64 * 4 * 3 * nf
-                chunk = max(1, min(len(idxs), int(self.max_batch_bytes // max(1, per_image))))
+                chunk = max(1, min(len(idxs), 32 // nf, int(self.max_batch_bytes // max(1, per_image))))
                 for c0 in range(0, len(idxs), chunk):
                     sub = idxs[c0:c0 + chunk]
                     data, info = self._level_batch([dev_images[i] for i in sub], s, flips)
                     self.net.forward_body(data)
-                    for j, i in enumerate(sub):
-                        for f, fl in enumerate(flips):
-                            self.net.run_tail(j * nf + f, info, dets=b["dets"][i], pass_offsets=b["offs"][i],
-                                              pass_idx=li * nf + f, det_cap=b["cap"], flip=fl, det_thresh=cfg.thresh)
+                    self.net.run_tail_batched(nf, info, b["dets"], b["offs"], image_base=sub[0], passes_total=passes,
+                                              pass_base=li * nf, det_cap=b["cap"], det_thresh=cfg.thresh)
         torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])
         method = 1 if cfg.nms_method == "BBOX_VOTE" else 0
         if cfg.nms_method not in ("BBOX_VOTE", "NMS"):
@@ -170,15 +175,18 @@ class Detector:
         """Device results -> list of (M,5) arrays ``[x1,y1,x2,y2,score]`` (float64 for BBOX_VOTE, as
         ``bbox_vote`` returns; float32 rows of ``dets`` for NMS)."""
         counts = b["out_count"][:B].cpu().numpy()
-        out = []
+        slots = []
         if self.cfg.nms_method == "BBOX_VOTE":
             host = b["out_dets"][:B].cpu().numpy()
-            for i in range(B):
-                out.append(host[i, :counts[i]].astype(np.float64))
+            for k in range(B):
+                slots.append(host[k, :counts[k]].astype(np.float64))
         else:
-            for i in range(B):
-                idx = b["out_idx"][i, :int(counts[i])].long()
-                out.append(b["dets"][i].index_select(0, idx).cpu().numpy())
+            for k in range(B):
+                idx = b["out_idx"][k, :int(counts[k])].long()
+                slots.append(b["dets"][k].index_select(0, idx).cpu().numpy())
+        out = [None] * B
+        for k, img_i in enumerate(b.get("order", range(B))):
+            out[img_i] = slots[k]
         return out
 
     def detect(self, images: List[np.ndarray]) -> List[np.ndarray]:
@@ -188,5 +196,6 @@ class Detector:
 
     def raw_detections(self, b, i: int) -> np.ndarray:
         """Pre-vote detections of image i (concatenated passes, score > thresh), for parity checks."""
-        n = int(b["offs"][i, -1].item())
-        return b["dets"][i, :n].cpu().numpy()
+        k = list(b.get("order", range(i + 1))).index(i)
+        n = int(b["offs"][k, -1].item())
+        return b["dets"][k, :n].cpu().numpy()

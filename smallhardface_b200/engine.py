@@ -443,6 +443,53 @@ class GpuNet:
         T[t["box_blob"]] = buf["delta"].view(1, 4 * A, H, W)
         return buf["out_boxes"], buf["out_probs"], meta32[1:2]
 
+    def run_tail_batched(self, nf, im_info, dets, pass_offsets, image_base, passes_total, pass_base, det_cap,
+                         det_thresh=0.05):
+        """Detection tail of every image of the last ``forward_body`` batch in three launches (decode, one sort,
+        gather).  Batch slot ``j*nf + f`` is image ``image_base + j`` of ``dets`` / ``pass_offsets``, pass ``f``
+        (0 plain, 1 mirrored)."""
+        t = self.tail
+        T = self.tensors
+        dev = self.device
+        A, Cf = t["A"], t["C"]
+        feats = [T[f] for f in t["feats"]]
+        f0 = feats[0]
+        N, H, W = f0.n, f0.h, f0.w
+        if N % nf:
+            raise L.ShfError("batch of %d is not a multiple of %d passes per image" % (N, nf))
+        hw, n = H * W, H * W * A
+        key = (N, n)
+        buf = getattr(self, "_tailbatch", {}).get(key)
+        if buf is None:
+            ws_bytes = int(L.load().shf_sort_keys_workspace(N * n))
+            buf = dict(prob=torch.empty((N, 2 * A, H, W), dtype=torch.float32, device=dev),
+                       delta=torch.empty((N, 4 * A, H, W), dtype=torch.float32, device=dev),
+                       boxes=torch.empty((N, n, 4), dtype=torch.float32, device=dev),
+                       keys=torch.empty((N * n,), dtype=torch.int64, device=dev),
+                       skeys=torch.empty((N * n,), dtype=torch.int64, device=dev),
+                       count=torch.zeros((N,), dtype=torch.int32, device=dev),
+                       best=torch.zeros((N,), dtype=torch.int64, device=dev),
+                       ws=torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev), ws_bytes=ws_bytes)
+            if not hasattr(self, "_tailbatch"):
+                self._tailbatch = {}
+            self._tailbatch[key] = buf
+        st = _stream()
+        fp = (C.c_void_p * A)(*[f.t.data_ptr() for f in feats])
+        ap = t["anchors"].ctypes.data_as(C.POINTER(C.c_float))
+        im_h, im_w, im_scale = float(im_info[0]), float(im_info[1]), float(im_info[2])
+        min_size = float(F32(self.cfg["min_size"]) * F32(im_scale))
+        topn = self.cfg["pre_nms_topn"] if self.cfg["pre_nms_topn"] > 0 else n
+        L.call("shf_head_decode_batched", fp, N * hw * Cf, hw * Cf, N, A, _ptr(t["wc"]), _ptr(t["bc"]), _ptr(t["wb"]),
+               _ptr(t["bb"]), ap, H, W, Cf, t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])),
+               _ptr(buf["prob"]), _ptr(buf["delta"]), _ptr(buf["boxes"]), _ptr(buf["keys"]), _ptr(buf["count"]),
+               _ptr(buf["best"]), st)
+        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), N * n, _ptr(buf["ws"]), buf["ws_bytes"], st)
+        L.call("shf_gather_dets_batched", _ptr(buf["skeys"]), _ptr(buf["count"]), _ptr(buf["best"]), _ptr(buf["prob"]),
+               _ptr(buf["boxes"]), A, hw, min(topn, n), N // nf, nf, _ptr(dets), _ptr(pass_offsets), int(image_base),
+               int(passes_total), int(pass_base), int(det_cap), float(F32(im_w)), float(F32(im_scale)),
+               float(F32(det_thresh)), st)
+        self.launches += 7
+
     # -- blob access ---------------------------------------------------------------------------------------
     def blob_nchw(self, name: str) -> torch.Tensor:
         """fp32 NCHW device tensor for a materialised blob (what ``Blob.data`` exposes in Caffe)."""

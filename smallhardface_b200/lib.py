@@ -38,6 +38,12 @@ SIGNATURES = {
     "shf_head_decode": (c_int, [C.POINTER(c_void_p), c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 C.POINTER(c_float), c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "shf_head_decode_batched": (c_int, [C.POINTER(c_void_p), c_ll, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        C.POINTER(c_float), c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "shf_gather_dets_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                                        c_void_p]),
     "shf_sort_keys_workspace": (c_ll, [c_int]),
     "shf_sort_keys": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
     "shf_proposal_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

@@ -147,3 +147,17 @@ def test_detector_pyramid_flip_vs_oracle(nets, method):
     else:
         keep = OP.nms(raw, 0.4, OP.NMS_CPU)
         assert np.array_equal(got, raw[keep])
+
+
+def test_detector_mixed_sizes_batch_equals_individual(nets):
+    """Images of different sizes in one call are grouped per shape and batched per level; every image must get
+    exactly the result it gets alone (and come back in call order)."""
+    dil, proto, model, gnet, onet = nets
+    cfg = DetectConfig(scales=(100, 300, 600))
+    det = Detector(proto, model, "cuda:0", cfg)
+    ims = [deploy.synthetic_image(s, hw) for s, hw in [(11, (96, 128)), (12, (80, 80)), (13, (96, 128)), (14, (80, 80)), (15, (64, 112))]]
+    together = det.detect(ims)
+    for im, res in zip(ims, together):
+        alone = det.detect([im])[0]
+        assert res.shape == alone.shape and np.array_equal(res, alone)
+    assert len({r.shape[0] for r in together}) > 1
