@@ -32,8 +32,11 @@ template <int COUT>
 __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                          const float* __restrict__ bias, __half* __restrict__ out,
                                                          int N, int H, int W, int relu) {
-  // Register-blocked: one thread = two horizontally adjacent output pixels x all COUT channels, 16 channels at a
-  // time; weights come from shared memory as float4 (one LDS.128 feeds 8 FMAs), inputs through the read-only path.
+  // Work split chosen for the STORE side (this layer writes 256 B per pixel and reads 12): four lanes share a run of
+  // four horizontally adjacent pixels, each lane owning 16 of the 64 output channels.  A quad therefore writes each
+  // pixel's 128-byte hi row (and lo row) as one full cache line, and one warp-wide store instruction covers 8 lines.
+  // Register blocking 4 pixels x 16 channels: one LDS.128 of weights feeds 16 FMAs.
+  static_assert(COUT == 64, "lane -> channel mapping assumes 64 output channels");
   __shared__ float4 ws[27][COUT / 4];     // [c*9 + r*3 + s][o/4]
   __shared__ float bs[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
@@ -42,17 +45,17 @@ __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int WP = (W + 1) / 2;                    // pixel pairs per row
-  const long long npairs = (long long)N * H * WP;
+  const int part = threadIdx.x & 3;              // channels [16*part, 16*part + 16)
+  const int WG = (W + 3) / 4;                    // 4-pixel groups per row
+  const long long ngroups = (long long)N * H * WG;
   const size_t plane = (size_t)N * H * W * COUT;
-  for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < npairs;
-       pr += (long long)gridDim.x * blockDim.x) {
-    const int xp = (int)(pr % WP);
-    const int y = (int)((pr / WP) % H);
-    const int n = (int)(pr / ((long long)WP * H));
-    const int x = xp * 2;
-    const bool has2 = (x + 1 < W);
-    float v[3][3][4];                            // [c][r][columns x-1 .. x+2]
+  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; g < ngroups;
+       g += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const int xg = (int)(g % WG);
+    const int y = (int)((g / WG) % H);
+    const int n = (int)(g / ((long long)WG * H));
+    const int x = xg * 4;
+    float v[3][3][6];                            // [c][r][columns x-1 .. x+4]
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -60,52 +63,51 @@ __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict
         const int iy = y + r - 1;
         const float* row = in + (((size_t)n * 3 + c) * H + iy) * W;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 6; ++q) {
           const int ix = x + q - 1;
           v[c][r][q] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(row + ix) : 0.f;
         }
       }
-    const size_t pix = ((size_t)n * H + y) * W + x;
-    __half* ohi = out + pix * COUT;
-    __half* olo = ohi + plane;
-#pragma unroll 1
-    for (int o0 = 0; o0 < COUT; o0 += 16) {
-      float a0[16], a1[16];
+    float acc[4][16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+    for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+      for (int j = 0; j < 16; ++j) acc[px][j] = 0.f;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            const float p0 = v[c][r][t], p1 = v[c][r][t + 1];
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 wv = ws[c * 9 + r * 3 + t][o0 / 4 + g];
-              a0[4 * g + 0] = fmaf(p0, wv.x, a0[4 * g + 0]); a1[4 * g + 0] = fmaf(p1, wv.x, a1[4 * g + 0]);
-              a0[4 * g + 1] = fmaf(p0, wv.y, a0[4 * g + 1]); a1[4 * g + 1] = fmaf(p1, wv.y, a1[4 * g + 1]);
-              a0[4 * g + 2] = fmaf(p0, wv.z, a0[4 * g + 2]); a1[4 * g + 2] = fmaf(p1, wv.z, a1[4 * g + 2]);
-              a0[4 * g + 3] = fmaf(p0, wv.w, a0[4 * g + 3]); a1[4 * g + 3] = fmaf(p1, wv.w, a1[4 * g + 3]);
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = ws[c * 9 + r * 3 + t][part * 4 + q];
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              const float pv = v[c][r][t + px];
+              acc[px][4 * q + 0] = fmaf(pv, wv.x, acc[px][4 * q + 0]);
+              acc[px][4 * q + 1] = fmaf(pv, wv.y, acc[px][4 * q + 1]);
+              acc[px][4 * q + 2] = fmaf(pv, wv.z, acc[px][4 * q + 2]);
+              acc[px][4 * q + 3] = fmaf(pv, wv.w, acc[px][4 * q + 3]);
             }
           }
+    const size_t pix0 = ((size_t)n * H + y) * W + x;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (x + px >= W) break;
+      __half* ohi = out + (pix0 + px) * COUT + part * 16;
+      __half* olo = ohi + plane;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        __half hi[8], lo[8], hi2[8], lo2[8];
+        __half hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float t0 = a0[h * 8 + j] + bs[o0 + h * 8 + j];
-          float t1 = a1[h * 8 + j] + bs[o0 + h * 8 + j];
-          if (relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+          float t0 = acc[px][h * 8 + j] + bs[part * 16 + h * 8 + j];
+          if (relu) t0 = fmaxf(t0, 0.f);
           split_h2(t0, hi[j], lo[j]);
-          split_h2(t1, hi2[j], lo2[j]);
         }
-        *reinterpret_cast<uint4*>(ohi + o0 + h * 8) = pack8(hi);
-        *reinterpret_cast<uint4*>(olo + o0 + h * 8) = pack8(lo);
-        if (has2) {
-          *reinterpret_cast<uint4*>(ohi + COUT + o0 + h * 8) = pack8(hi2);
-          *reinterpret_cast<uint4*>(olo + COUT + o0 + h * 8) = pack8(lo2);
-        }
+        *reinterpret_cast<uint4*>(ohi + h * 8) = pack8(hi);
+        *reinterpret_cast<uint4*>(olo + h * 8) = pack8(lo);
       }
     }
   }
@@ -397,7 +399,7 @@ int grid_for(long long total, int block) {
 extern "C" int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch,
                             int H, int W, int cout, int relu, void* stream) {
   SHF_REQUIRE(cout == 64, "shf_conv1_c3: Cout=%d (the deploy nets' conv1_1 has 64)", cout);
-  const long long npix = (long long)batch * H * ((W + 1) / 2);      // one thread per pixel pair
+  const long long npix = (long long)batch * H * ((W + 3) / 4) * 4;  // four threads per run of four pixels
   conv3x3_c3_kernel<64><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(in_nchw, w_oihw, bias, (__half*)out_h2,
                                                                                batch, H, W, relu);
   SHF_LAUNCH_CHECK();
