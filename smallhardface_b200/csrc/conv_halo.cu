@@ -27,7 +27,7 @@ int shf_conv_pertap_impl(const void* in_h2, const void* w_h2, const float* bias,
 int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
-                         void* stream);
+                         int ctas, void* stream);
 
 namespace {
 
@@ -263,10 +263,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // implementation selector (shf_set_conv_impl; tests / tuning):
 //   0 = v1 per-tap loads (conv_igemm.cu)      1 = halo, XW = 16        3 = halo, XW = 8 + 2d (default)
 //   5 = as 3 but 64-channel N tiles whenever Cout <= 128 (two CTAs per SM)
-//   7 = v3 persistent streaming-drain kernel (conv_stream.cu)
+//   7 = v3 persistent streaming-drain kernel (conv_stream.cu), one CTA per tile
+//   8 = the same kernel on CTA pairs (cta_group::2, weight stage split across the two SMs of a TPC) (default)
 //   2 / 4 = as 1 / 3 with descriptor base_offset = (start >> 7) & 7 -- measured WRONG on B200: the UMMA swizzle is a
 //           function of the absolute smem address, base_offset must stay 0 (kept only as a regression probe)
-int g_conv_impl = 7;
+int g_conv_impl = 8;
 
 template <int BN>
 int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HaloParams& p, int batch,
@@ -293,11 +294,11 @@ extern "C" int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const fl
   SHF_REQUIRE(pool_out_h2 != nullptr, "shf_conv_igemm_pool: pool_out_h2 is NULL");
   return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                               out_channel_offset, out_scale, relu, pool_out_h2, pool_channels_total,
-                              pool_channel_offset, stream);
+                              pool_channel_offset, g_conv_impl == 7 ? 1 : 2, stream);
 }
 
 extern "C" int shf_set_conv_impl(int impl) {
-  SHF_REQUIRE(impl >= 0 && impl <= 7, "shf_set_conv_impl: %d", impl);
+  SHF_REQUIRE(impl >= 0 && impl <= 8, "shf_set_conv_impl: %d", impl);
   g_conv_impl = impl;
   return 0;
 }
@@ -306,9 +307,9 @@ extern "C" int shf_set_conv_impl(int impl) {
 extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H,
                               int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
                               int out_channel_offset, float out_scale, int relu, void* stream) {
-  if (g_conv_impl == 7)
+  if (g_conv_impl >= 7)
     return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
-                                out_channel_offset, out_scale, relu, nullptr, 0, 0, stream);
+                                out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_impl == 7 ? 1 : 2, stream);
   if (g_conv_impl == 0)
     return shf_conv_pertap_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                                 out_channel_offset, out_scale, relu, stream);

@@ -17,6 +17,13 @@
 //    accumulations against 96 (v2) or 864 (a single accumulator over K = 4608).
 //  * epilogue writes NHWC hi/lo rows straight from registers (each thread owns one pixel: 2*BN contiguous bytes
 //    per plane), so no staging buffer competes with the operand rings for shared memory.
+//  * CTA pairs (CTAS = 2, the default): a cluster of two CTAs works on two horizontally adjacent pixel tiles with ONE
+//    tcgen05.mma.cta_group::2 stream issued by the leader.  Each CTA loads only HALF of every weight stage (its
+//    half of the output channels, hi and lo planes) -- the tensor cores read the other half from the peer's shared
+//    memory -- so L2->SM weight traffic per SM halves.  r01 profiles showed that traffic (not DRAM, not the MMA
+//    pipe) bounding the single-CTA kernel at ~9 TB/s.  Barriers: "full" lives in the leader and is credited by both
+//    CTAs' TMA loads; "empty"/"accumulator full" are multicast commits to both CTAs; "accumulator drained" collects
+//    the eight epilogue warps of the pair in the leader.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -27,7 +34,7 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kTH = 16, kTW = 8;
 constexpr int kChunkK = 64;
-constexpr int kMaxA = 4, kMaxB = 6;
+constexpr int kMaxA = 4, kMaxB = 8;
 
 struct StreamParams {
   int H, W, batch;
@@ -38,6 +45,7 @@ struct StreamParams {
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int chunks_per_phase;       // G
   int ctot, cout_offset, relu;
+  int probe;                  // timing probes (SHF_PROBE_MODE): 1 = two N=BN f16 MMAs per k-step, 2 = f16 + f8f6f4
   float out_scale;
   const float* bias;
   __half* out;                // h2 destination tensor base (plane 0); plane 1 at + plane_elems (nullptr: skip)
@@ -51,7 +59,7 @@ struct StreamParams {
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(256, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const StreamParams p) {
@@ -71,7 +79,11 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto a_stage = [&](int s) { return smem_base + (uint32_t)(s * p.a_bytes); };
   auto b_stage = [&](int s) { return smem_base + (uint32_t)(p.na * p.a_bytes + s * p.b_bytes); };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: ptxas then KNOWS it is warp-uniform and keeps the role branches, loop counters and
+  // MMA descriptors in uniform registers (otherwise every tcgen05.mma operand costs an R2UR in the issue loop)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs of the pair)
+  const int cta_lin = (int)(blockIdx.x / CTAS), cta_cnt = (int)(gridDim.x / CTAS);   // persistent walk over (pair) tiles
   constexpr uint32_t kTmemCols = 512;          // whole tensor memory: two sets of 2*BN columns at fixed addresses
   constexpr uint32_t kSetCols = 2 * BN;
 
@@ -80,14 +92,14 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kMaxA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < kMaxB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4 * CTAS); }
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   if (*tmem_slot != 0u) __trap();              // the full allocation starts at column 0
   const int phases_per_tile = (p.cin_chunks + p.chunks_per_phase - 1) / p.chunks_per_phase;
@@ -96,7 +108,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto decode_tile = [&](int t, int& nt, int& x0, int& y0, int& img) {
     nt = t % p.n_tiles;
     int q = t / p.n_tiles;
-    x0 = (q % p.tiles_x) * kTW;
+    x0 = ((q % p.tiles_x) * CTAS + (int)rank) * kTW;      // p.tiles_x counts tile PAIRS when CTAS == 2
     q /= p.tiles_x;
     y0 = (q % p.tiles_y) * kTH;
     img = q / p.tiles_y;
@@ -106,48 +118,66 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== TMA producer: weight stages [B_hi ; B_lo], one per (chunk, tap) =====================
     if (lane == 0) {
       int itb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
         int nt, x0, y0, img;
         decode_tile(t, nt, x0, y0, img);
         for (int cc = 0; cc < p.cin_chunks; ++cc)
           for (int tap = 0; tap < p.taps; ++tap, ++itb) {
             const int sb = itb % p.nb;
             mbar_wait(empty_b(sb), ((itb / p.nb) & 1) ^ 1);
-            mbar_arrive_expect_tx(full_b(sb), p.b_bytes);
-            tma_load_4d(b_stage(sb), &tmap_b, full_b(sb), cc * kChunkK, nt * BN, tap, 0);
+            if (CTAS == 2) {
+              // both CTAs credit the LEADER's barrier; each loads its half of the output channels (hi and lo plane)
+              if (rank == 0) mbar_arrive_expect_tx(full_b(sb), 2 * p.b_bytes);
+              tma_load_4d_pair(b_stage(sb), &tmap_b, mapa_shared(full_b(sb), 0), cc * kChunkK,
+                               nt * BN + (int)rank * (BN / 2), tap, 0);
+            } else {
+              mbar_arrive_expect_tx(full_b(sb), p.b_bytes);
+              tma_load_4d(b_stage(sb), &tmap_b, full_b(sb), cc * kChunkK, nt * BN, tap, 0);
+            }
           }
       }
+      if (CTAS == 2)      // tail: the leader's multicast commits must have landed here before this CTA may exit
+        for (int k = 0; k < p.nb; ++k, ++itb) mbar_wait(empty_b(itb % p.nb), ((itb / p.nb) & 1) ^ 1);
     }
   } else if (warp == 3) {
     // ===================== TMA producer: activation halos, one per 64-channel chunk =====================
     if (lane == 0) {
       int ita = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
         int nt, x0, y0, img;
         decode_tile(t, nt, x0, y0, img);
         for (int cc = 0; cc < p.cin_chunks; ++cc, ++ita) {
           const int sa = ita % p.na;
           mbar_wait(empty_a(sa), ((ita / p.na) & 1) ^ 1);
-          mbar_arrive_expect_tx(full_a(sa), p.a_tx);
-          tma_load_5d(a_stage(sa), &tmap_a, full_a(sa), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
+          if (CTAS == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(full_a(sa), 2 * p.a_tx);
+            tma_load_5d_pair(a_stage(sa), &tmap_a, mapa_shared(full_a(sa), 0), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
+          } else {
+            mbar_arrive_expect_tx(full_a(sa), p.a_tx);
+            tma_load_5d(a_stage(sa), &tmap_a, full_a(sa), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
+          }
         }
       }
+      if (CTAS == 2)
+        for (int k = 0; k < p.na; ++k, ++ita) mbar_wait(empty_a(ita % p.na), ((ita / p.na) & 1) ^ 1);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp converged, one elected lane issues) =====================
-    constexpr uint32_t idesc_wide = umma_idesc_f16(kTileM, 2 * BN);     // A_hi x [B_hi ; B_lo]
-    constexpr uint32_t idesc_half = umma_idesc_f16(kTileM, BN);         // A_lo x B_hi (and the phase-opening hi*hi)
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (warp converged, one elected lane issues; leader CTA only) =====================
+    constexpr uint32_t idesc_wide = umma_idesc_f16(kTileM * CTAS, 2 * BN);     // A_hi x [B_hi ; B_lo]      (CTAS == 1)
+    constexpr uint32_t idesc_half = umma_idesc_f16(kTileM * CTAS, BN);         // one operand-plane pair
+    constexpr uint32_t idesc_f8 = umma_idesc_f8(kTileM * CTAS, BN, 1u, 0u);    // timing probe only
     const uint32_t a_hi32 = (uint32_t)((p.xw * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
     constexpr uint32_t b_hi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t lbo = 1u << 16;
+    constexpr uint32_t b_plane16 = (uint32_t)((BN / CTAS) * 128) >> 4;           // hi rows -> lo rows of a weight stage
     const uint32_t a_plane16 = ((uint32_t)(p.xh * p.xw) * 128u) >> 4;
     const int ktaps = (p.taps == 9) ? 3 : 1;
     int ita = 0, itb = 0, gp = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
       for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
         const int set = gp & 1;
         const uint32_t d_main = (uint32_t)set * kSetCols;
-        mbar_wait(acc_empty(set), ((gp >> 1) & 1) ^ 1);           // drained by the epilogue warps
+        mbar_wait(acc_empty(set), ((gp >> 1) & 1) ^ 1);           // drained by the epilogue warps (of both CTAs)
         tc_fence_after();
         const int c_begin = ph * p.chunks_per_phase;
         const int c_end = min(c_begin + p.chunks_per_phase, p.cin_chunks);
@@ -164,21 +194,39 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t a_off = (uint32_t)((r * p.dil) * p.xw + s * p.dil) * 128u;
             uint32_t a_lo32 = (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo;
             uint32_t b_lo32 = ((b_stage(sb) & 0x3FFFFu) >> 4) | lbo;
+            if (CTAS == 2) {
+              // the pair's weight stage is split by output channel, so hi and lo rows are separate N = BN operands:
+              //   main += A_hi x B_hi ;  cross += A_hi x B_lo ;  cross += A_lo x B_hi
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) {
-              // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
-              umma_f16_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
-              // cross += A_lo x B_hi
-              umma_f16_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
-              opened = 1u;
-              a_lo32 += 2; b_lo32 += 2;
+              for (int k = 0; k < kChunkK / 16; ++k) {
+                umma_f16_pair_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+                if (p.probe == 2) {
+                  umma_f8_pair_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, opened);
+                } else {
+                  umma_f16_pair_elect_lohi(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
+                  umma_f16_pair_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+                }
+                opened = 1u;
+                a_lo32 += 2; b_lo32 += 2;
+              }
+              umma_commit_pair_elect(empty_b(sb));
+            } else {
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) {
+                // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
+                umma_f16_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
+                // cross += A_lo x B_hi
+                umma_f16_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+                opened = 1u;
+                a_lo32 += 2; b_lo32 += 2;
+              }
+              umma_commit_elect(empty_b(sb));
             }
-            umma_commit_elect(empty_b(sb));
             if (++s == ktaps) { s = 0; ++r; }
           }
-          umma_commit_elect(empty_a(sa));
+          if (CTAS == 2) umma_commit_pair_elect(empty_a(sa)); else umma_commit_elect(empty_a(sa));
         }
-        umma_commit_elect(acc_full(set));
+        if (CTAS == 2) umma_commit_pair_elect(acc_full(set)); else umma_commit_elect(acc_full(set));
       }
     }
   } else if (warp >= 4) {
@@ -187,8 +235,10 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int m = w * 32 + lane;                 // accumulator row = pixel (y_local * 8 + x_local)
     const uint32_t lane_addr = (uint32_t)(w * 32) << 16;
     const float scale = p.out_scale;
+    const uint32_t drained0 = (CTAS == 2) ? mapa_shared(acc_empty(0), 0) : acc_empty(0);   // in the leader
+    const uint32_t drained1 = (CTAS == 2) ? mapa_shared(acc_empty(1), 0) : acc_empty(1);
     int gp = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
       int nt, x0, y0, img;
       decode_tile(t, nt, x0, y0, img);
       float acc[BN];
@@ -211,7 +261,10 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cnt(acc_empty(set));          // 4 warps -> the set is free again
+        if (lane == 0) {                                          // 4 (x2) warps -> the set is free again
+          if (CTAS == 2) mbar_arrive_cluster(set ? drained1 : drained0);
+          else mbar_arrive_cnt(acc_empty(set));
+        }
       }
       // ---- epilogue for this tile: bias, ReLU, (2x2 max pool), split to hi/lo, NHWC rows straight to global memory ----
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
@@ -270,22 +323,38 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(0u, kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(0u, kTmemCols); else tmem_dealloc(0u, kTmemCols);
   }
 }
 
-template <int BN>
+template <int BN, int CTAS>
 int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
                   cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  conv_stream_kernel<BN><<<grid, 256, smem_bytes, stream>>>(ta, tb, p);
+  if (CTAS == 1) {
+    conv_stream_kernel<BN, CTAS><<<grid, 256, smem_bytes, stream>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CTAS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS>, ta, tb, p));
+  }
   SHF_LAUNCH_CHECK();
   return 0;
 }
@@ -306,7 +375,8 @@ int sm_count() {
 int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
-                         void* stream) {
+                         int ctas, void* stream) {
+  SHF_REQUIRE(ctas == 1 || ctas == 2, "shf_conv_igemm: %d CTAs per tile group", ctas);
   SHF_REQUIRE(out_h2 != nullptr || pool_out_h2 != nullptr, "shf_conv_igemm: no destination");
   if (pool_out_h2)
     SHF_REQUIRE(H % 2 == 0 && W % 2 == 0 && pool_channel_offset % 8 == 0 && pool_channels_total % 8 == 0 &&
@@ -331,7 +401,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.xh = kTH + 2 * p.pad;
   p.a_tx = 2 * p.xh * p.xw * 128;
   p.a_bytes = (p.a_tx + 1023) & ~1023;
-  p.b_bytes = 2 * bn * 128;
+  p.b_bytes = 2 * (bn / ctas) * 128;          // per CTA: its share of the output channels, hi + lo plane
   const int budget = 227 * 1024 - 1024 - 512;
   p.na = (p.taps == 1) ? kMaxA : 2;
   while (p.na > 1 && p.na * p.a_bytes + 3 * p.b_bytes > budget) --p.na;
@@ -339,7 +409,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   if (p.nb > kMaxB) p.nb = kMaxB;
   if (const char* e = getenv("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
   SHF_REQUIRE(p.nb >= 2, "shf_conv_igemm: halo tile of %d bytes leaves no room for the weight ring", p.a_bytes);
-  p.tiles_x = (W + kTW - 1) / kTW;
+  p.tiles_x = ((W + kTW - 1) / kTW + ctas - 1) / ctas;          // tile pairs along x when ctas == 2
   p.tiles_y = (H + kTH - 1) / kTH;
   p.n_tiles = cout / bn;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * batch;
@@ -348,6 +418,8 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.ctot = out_channels_total;
   p.cout_offset = out_channel_offset;
   p.relu = relu;
+  p.probe = 0;
+  if (const char* e = getenv("SHF_PROBE_MODE")) p.probe = atoi(e);
   p.out_scale = out_scale;
   p.bias = bias;
   p.out = reinterpret_cast<__half*>(out_h2);
@@ -366,10 +438,13 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   }
   {
     uint64_t d[4] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)p.taps, 2};
-    uint32_t b[4] = {64, (uint32_t)bn, 1, 2};
+    uint32_t b[4] = {64, (uint32_t)(bn / ctas), 1, 2};
     if (int e = shf_encode_f16_map(&tb, const_cast<void*>(w_h2), 4, d, b, "weights")) return e;
   }
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  const int groups = sm_count() / ctas;
+  const int grid = (p.total_tiles < groups ? p.total_tiles : groups) * ctas;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return bn == 128 ? launch_stream<128>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64>(ta, tb, p, smem_bytes, grid, st);
+  if (ctas == 2)
+    return bn == 128 ? launch_stream<128, 2>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64, 2>(ta, tb, p, smem_bytes, grid, st);
+  return bn == 128 ? launch_stream<128, 1>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64, 1>(ta, tb, p, smem_bytes, grid, st);
 }

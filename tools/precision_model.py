@@ -1,0 +1,139 @@
+"""CPU model of the tensor-core operand formats (runs without a GPU; uses oracle/ as the fp32 yardstick).
+
+Question it answers: how far do the final boxes / scores of one pyramid level move, in raw-image px, when every
+tcgen05 convolution consumes operands in a given reduced format?  Products are accumulated in float64 here, so
+only the OPERAND rounding is modelled (the accumulation error of the tensor core is measured on the GPU).
+
+schemes:
+  exact      fp32 operands (yardstick against itself: 0)
+  f16        single fp16 operand planes                       x ~ rn16(x), w ~ rn16(w)
+  h2         split fp16 (hi + lo, 3 MMAs: hi*hi + hi*lo + lo*hi)
+  h2f8       fp16 main term + fp8 correction term:
+               x = ah + al,  ah = rn16(x),  al8 = e5m2(al * 2^10),  ah8 = e5m2(ah)
+               w*2^k = wh + wl, wh = rn16,  wh8 = e4m3(wh * 2^-10), wl8 = e4m3(wl)
+               y = ah*wh  +  al8*wh8 + ah8*wl8        (one kind::f16 MMA + one K=32 kind::f8f6f4 MMA per 16 channels)
+
+usage: python tools/precision_model.py [level ...]      (levels = TEST.SCALES entries, default 100 300)
+"""
+import math
+import os
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from smallhardface_b200 import deploy
+from oracle.net import OracleNet
+from oracle import detect as OD, preprocess as PRE, layers as OL
+
+F64 = torch.float64
+
+
+def rn16(t):
+    return t.to(torch.float16).to(F64)
+
+
+def e5m2(t):
+    return t.to(torch.float32).to(torch.float8_e5m2).to(F64)
+
+
+def e4m3(t):
+    return t.to(torch.float32).clamp(-448, 448).to(torch.float8_e4m3fn).to(F64)
+
+
+def quant_act(x, scheme):
+    """value the NEXT consumer sees for an activation stored in `scheme`'s format"""
+    x = x.to(F64)
+    if scheme == "exact":
+        return x
+    ah = rn16(x)
+    if scheme == "f16":
+        return ah
+    al = x - ah
+    if scheme == "h2":
+        return ah + rn16(al)
+    if scheme == "h2f8":
+        return ah + e5m2(al * 1024.0) / 1024.0
+    if scheme == "h2f8e4":          # e4m3 residual with a static 2^8 scale (needs |x| < 2^12)
+        return ah + e4m3(al * 256.0) / 256.0
+    raise ValueError(scheme)
+
+
+def make_conv(scheme):
+    real_conv = OL.conv
+
+    def conv(x, w, b=None, pad=(0, 0), stride=(1, 1), dilation=(1, 1), group=1, engine="sgemm", **kw):
+        cin = w.shape[1]
+        if cin % 64 or w.shape[0] % 64 or scheme == "exact":          # conv1_1, cls/bbox 1x1: fp32 SIMT kernels
+            xq = quant_act(torch.from_numpy(np.ascontiguousarray(x)), scheme if cin % 64 == 0 else "exact")
+            return real_conv(xq.to(torch.float32).numpy(), w, b, pad, stride, dilation, group, engine="torch")
+        xt = torch.from_numpy(np.ascontiguousarray(x)).to(F64)
+        wt = torch.from_numpy(np.ascontiguousarray(w)).to(F64)
+        amax = float(wt.abs().max())
+        k = int(14 - math.ceil(math.log2(amax)))
+        ws = wt * 2.0 ** k
+        cv = lambda a, bb: torch.nn.functional.conv2d(a, bb, None, stride=stride, padding=pad, dilation=dilation)
+        ah = rn16(xt)
+        al = xt - ah
+        wh = rn16(ws)
+        wl = ws - wh
+        if scheme == "f16":
+            y = cv(ah, wh)
+        elif scheme == "h2":
+            all_, wll = rn16(al), rn16(wl)
+            y = cv(ah, wh) + cv(ah, wll) + cv(all_, wh)
+        elif scheme in ("h2f8", "h2f8e4"):
+            if scheme == "h2f8":
+                al8 = e5m2(al * 1024.0)
+                ah8 = e5m2(ah)
+            else:
+                al8 = e4m3(al * 256.0) * 4.0
+                ah8 = e5m2(ah)
+            wh8 = e4m3(wh / 1024.0)
+            wl8 = e4m3(wl)
+            y = cv(ah, wh) + cv(al8, wh8) + cv(ah8, wl8)
+        else:
+            raise ValueError(scheme)
+        y = y * 2.0 ** (-k)
+        if b is not None:
+            y = y + torch.from_numpy(np.asarray(b)).to(F64)[None, :, None, None]
+        return y.to(torch.float32).numpy()
+
+    return conv
+
+
+def run_level(onet, im, lv, scheme):
+    s = PRE.pyramid_scales(im.shape, (lv, lv + 1))[0]
+    blob = PRE.get_image_blobs(im, [s])[0]
+    saved = OL.conv
+    OL.conv = make_conv(scheme)
+    try:
+        p, bx = OD.forward_level(onet, blob, s)
+    finally:
+        OL.conv = saved
+    return s, p, bx, onet.last_order.copy()
+
+
+def main():
+    levels = [int(a) for a in sys.argv[1:]] or [100, 300]
+    proto, model = deploy.write_synthetic_deployment(os.path.join(tempfile.gettempdir(), "shf_b200_deploy"), dilation=True)
+    onet = OracleNet(proto, model, engine="torch", fast=True)
+    im = deploy.synthetic_image(3)
+    for lv in levels:
+        s, p0, b0, o0 = run_level(onet, im, lv, "exact")
+        for scheme in ("f16", "h2", "h2f8", "h2f8e4"):
+            _, p1, b1, o1 = run_level(onet, im, lv, scheme)
+            # align rows by anchor index (order = anchor ids in descending score order)
+            m0 = {int(a): i for i, a in enumerate(o0)}
+            idx = [(m0[int(a)], j) for j, a in enumerate(o1) if int(a) in m0]
+            i0 = np.array([a for a, _ in idx]); i1 = np.array([b for _, b in idx])
+            db = np.abs(b0[i0] - b1[i1]).max() if len(idx) else float("nan")
+            ds = np.abs(p0[i0] - p1[i1]).max() if len(idx) else float("nan")
+            print("level %4d scale %.4f  %-7s rows %5d/%5d common %5d  score err %.2e  box err %.2e raw px (%.2e level px)"
+                  % (lv, s, scheme, len(o1), len(o0), len(idx), ds, db, db * s), flush=True)
+
+
+if __name__ == "__main__":
+    main()
