@@ -5,8 +5,13 @@
  * success, a negative code otherwise, with a human-readable message from shf_last_error().
  * Launches are asynchronous on `stream`; nothing synchronises unless stated.
  *
- * Activation format "h2": NHWC split-fp16, two planes [2][N][H][W][C] of __half with x = hi + lo
- * (hi = rn(x), lo = rn(x - hi)); C must be a multiple of 8 (16-byte rows for TMA).
+ * Activation tensors are NHWC, 4 bytes per element in two equally sized planes; every function that touches
+ * one takes the format of what it reads / writes:
+ *   SHF_FMT_H2  (0, "h2", precise): planes [2][N][H][W][C] of __half with x = hi + lo (hi = rn(x), lo = rn(x - hi));
+ *               C a multiple of 8 (16-byte rows for TMA).  The conv runs 3 fp16 MMAs per 16 input channels.
+ *   SHF_FMT_HF8 (1, "hf8", fast): plane 0 = hi as above; plane 1 = per pixel and 64-channel block, 64 bytes
+ *               e5m2((x - hi) * 2^10) then 64 bytes e5m2(hi); C (and channel windows) multiples of 64.  The conv
+ *               runs 1 fp16 + 1 fp8 (K = 32) MMA per 16 input channels; x is carried to ~2^-15 relative.
  * Each declaration cites the reference interface it stands in for (paths under the reference repo).
  */
 #ifndef SHF_B200_H
@@ -18,6 +23,9 @@
 extern "C" {
 #endif
 
+#define SHF_FMT_H2 0
+#define SHF_FMT_HF8 1
+
 const char* shf_last_error(void);
 int shf_abi_version(void);
 int shf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, long long* total_mem);
@@ -27,12 +35,14 @@ int shf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, lon
 /* ConvolutionLayer<float>::Forward (conv_layer.cpp:30-46 -> base_conv_layer.cpp:255-279) followed by the
  * in-place ReLULayer (relu_layer.cpp:9-19), for 3x3 (pad == dilation, stride 1) and 1x1 convolutions with
  * Cin, Cout multiples of 64.  tcgen05 implicit GEMM.  w_h2 [dev]: weights pre-packed as
- * [2 planes][taps][Cout][Cin] fp16 of (w * 2^k); out_scale = 2^-k.  The result lands in channels
+ * [2 planes][taps][Cout][Cin] fp16 of (w * 2^k) (in_format h2: hi / lo planes; in_format hf8: plane 1 holds, per
+ * (tap, Cout, 64-channel block), 64 bytes e4m3(hi * 2^-10) then 64 bytes e4m3(lo)); out_scale = 2^-k.
+ * in_format describes in_h2 AND w_h2, out_format what is written.  The result lands in channels
  * [out_channel_offset, +cout) of an h2 tensor with out_channels_total channels (ConcatLayer by construction,
  * concat_layer.cpp:47-74). */
 int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                    int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
-                   float out_scale, int relu, void* stream);
+                   float out_scale, int relu, int in_format, int out_format, void* stream);
 
 /* shf_conv_igemm + the PoolingLayer MAX 2x2/2 that follows it (pooling_layer.cpp:140-187) in one launch: the pooled
  * map goes to pool_out_h2 (N, H/2, W/2, pool_channels_total) at pool_channel_offset; out_h2 may be NULL when the
@@ -40,29 +50,31 @@ int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void*
 int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, void* pool_out_h2, int batch,
                         int H, int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
                         int out_channel_offset, int pool_channels_total, int pool_channel_offset, float out_scale,
-                        int relu, void* stream);
+                        int relu, int in_format, int out_format, void* stream);
 
-/* Tuning / test hook: selects the operand-staging strategy of shf_conv_igemm (same results, different smem traffic):
- * 0 = one TMA load per (tap, chunk); 1 = halo tile reused by all taps (default); 2-4 = halo variants under test. */
+/* Tuning / test hook: selects the kernel behind shf_conv_igemm (same results): 0 = v1, one TMA load per (tap, chunk);
+ * 1-5 = v2 halo-tile variants; 7 = v3 persistent streaming-drain kernel, one CTA per tile; 8 = v3 on CTA pairs
+ * (tcgen05 cta_group::2, the default).  0-5 only know the h2 format. */
 int shf_set_conv_impl(int impl);
 
 /* conv1_1: fp32 NCHW (N,3,H,W) [dev] -> h2 (N,H,W,64); weights OIHW fp32 [dev] (64,3,3,3), pad 1. */
 int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch, int H, int W,
-                 int cout, int relu, void* stream);
+                 int cout, int relu, int out_format, void* stream);
 
 /* PoolingLayer MAX 2x2 stride 2 (pooling_layer.cpp:79-123,140-187), ceil-mode output (H+1)/2 x (W+1)/2. */
-int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, void* stream);
+int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, int format, void* stream);
 
 /* DeconvolutionLayer with group == channels (deconv_layer.cpp:8-46; the net's conv5_256_up k4 s2 p1).
  * w [dev]: fp32 (C,1,k,k). Output size stride*(H-1)+k-2*pad, written at a channel offset like shf_conv_igemm. */
 int shf_deconv_depthwise(const void* in_h2, const float* w, void* out_h2, int batch, int H, int W, int C, int ksize,
-                         int stride, int pad, int out_channels_total, int out_channel_offset, void* stream);
+                         int stride, int pad, int out_channels_total, int out_channel_offset, int in_format,
+                         int out_format, void* stream);
 
 /* Blob boundary (caffe/python/caffe/_caffe.cpp:205-242 exposes blobs as fp32 NCHW arrays). */
 int shf_h2_to_nchw(const void* in_h2, float* out_nchw, int batch, int H, int W, int channels_total, int channel_offset,
-                   int channels, void* stream);
+                   int channels, int format, void* stream);
 int shf_nchw_to_h2(const float* in_nchw, void* out_h2, int batch, int channels, int H, int W, int channels_total,
-                   int channel_offset, void* stream);
+                   int channel_offset, int format, void* stream);
 
 /* ---- pre-processing (lib/utils/test_utils.py:29-46, lib/utils/blob.py:16-32, lib/test.py:30-38,147-155) -- */
 /* uint8 HWC BGR image [dev] -> one pyramid level: mean-subtract, bilinear resize by `scale` (cv2 fx=fy
@@ -74,7 +86,8 @@ int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float* out_chw, i
 /* ---- detection tail -------------------------------------------------------------------------- */
 /* cls_score*/bbox_pred* 1x1 convs + Concat/Reshape + SoftmaxLayer (softmax_layer.cpp:27-60) + the decode half of
  * ProposalLayer.forward (lib/layers/proposal_layer.py:96-173, lib/utils/bbox_transform.py:33-93).
- * feat_h2: host array of num_anchors [dev] pointers to ONE image's hi-plane rows (H,W,C) inside an h2 tensor;
+ * feat_h2: host array of num_anchors [dev] pointers to ONE image's hi-plane rows (H,W,C) inside an h2-FORMAT tensor
+ * (the head convs write h2 whatever format they read);
  * feat_plane_stride = elements between its hi and lo planes (N*H*W*C for a batch of N; 0 means H*W*C).
  * w_cls [A][2][C], b_cls [A][2], w_box [A][4][C], b_box [A][4], all fp32 [dev]; base_anchors: host [A][4].
  * Outputs [dev]: prob (2A,H,W) fp32 = cls_prob_reshape_output; delta (4A,H,W) = bbox_pred_output;
@@ -147,7 +160,7 @@ int shf_bbox_overlaps(const double* boxes, const double* query, int n, int k, in
 /* Validation only (not on the product path): direct fp32 convolution on h2 tensors, OIHW fp32 weights. */
 int shf_debug_conv_direct(const void* in_h2, const float* w_oihw, const float* bias, void* out_h2, int batch, int H,
                           int W, int cin, int cout, int ksize, int dilation, int pad, int out_channels_total,
-                          int out_channel_offset, int relu, void* stream);
+                          int out_channel_offset, int relu, int in_format, int out_format, void* stream);
 
 #ifdef __cplusplus
 }

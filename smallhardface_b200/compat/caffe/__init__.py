@@ -1,5 +1,5 @@
 """`import caffe` drop-in (see smallhardface_b200/pycaffe.py; reference: caffe/python/caffe/__init__.py:1-8)."""
-from smallhardface_b200.pycaffe import (Net, Blob, Layer, TRAIN, TEST, set_mode_gpu, set_mode_cpu, set_device,  # noqa: F401
+from smallhardface_b200.pycaffe import (Net, Blob, Layer, TRAIN, TEST, set_mode_gpu, set_mode_cpu, set_device, set_fast_min_scale,  # noqa: F401
                                         SGDSolver, NCCL, set_random_seed, set_solver_count, set_solver_rank,
                                         set_multiprocess, init_log, log)
 from . import proto  # noqa: F401

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,14 +36,118 @@ void shf_set_error(const char* fmt, ...);
 #define SHF_LAUNCH_CHECK() SHF_CUDA_CHECK(cudaGetLastError())
 
 // ----------------------------------------------------------------------------------------------
-// split-fp16 activation format: x = hi + lo, hi = rn_f16(x), lo = rn_f16(x - hi)  (|err| <= 2^-22 |x|)
-// stored as two NHWC planes [2][N][H][W][C] so one TMA box fetches both.
+// Activation formats.  Both are NHWC, 4 bytes per element in two equally sized planes, C a multiple of 8:
+//
+//  SHF_FMT_H2  ("h2", precise): x = hi + lo, hi = rn_f16(x), lo = rn_f16(x - hi)   (|err| <= 2^-22 |x|).
+//      planes [2][N][H][W][C] of __half; the conv issues hi*hi + hi*lo + lo*hi as three kind::f16 MMAs.
+//
+//  SHF_FMT_HF8 ("hf8", fast): plane 0 = hi = rn_f16(x) as above; plane 1 holds, per pixel and per block of 64
+//      channels, 64 bytes  al8 = e5m2((x - hi) * 2^10)  followed by 64 bytes  ah8 = e5m2(hi)  -- i.e. one 128-byte
+//      K = 128 row of 8-bit floats.  The conv issues hi*hi as ONE kind::f16 MMA and the first-order correction
+//      al*wh + ah*wl as ONE kind::f8f6f4 MMA (K = 32 per instruction, same issue time) against a weight plane laid
+//      out the same way ([wh8 = e4m3(wh * 2^-10) | wl8 = e4m3(wl)]): 2 MMAs per 16 channels instead of 3.
+//      x is recovered as hi + al8 * 2^-10 (|err| <~ 2^-15 |x|); C must be a multiple of 64.
+//      tools/precision_model.py quantifies what that costs in box / score accuracy per pyramid level.
 // ----------------------------------------------------------------------------------------------
+enum { SHF_FMT_H2 = 0, SHF_FMT_HF8 = 1 };
+
 SHF_DEVICE void split_h2(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
 }
 SHF_DEVICE float join_h2(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+
+SHF_DEVICE uint8_t f32_to_e5m2(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); }
+// e5m2 is the upper byte of the fp16 with the same value
+SHF_DEVICE float e5m2_to_f32(uint8_t b) { return __half2float(__ushort_as_half((unsigned short)((unsigned short)b << 8))); }
+SHF_DEVICE void split_hf8(float v, __half& hi, uint8_t& al8, uint8_t& ah8) {
+  hi = __float2half_rn(v);
+  const float h = __half2float(hi);
+  al8 = f32_to_e5m2((v - h) * 1024.f);
+  ah8 = f32_to_e5m2(h);
+}
+SHF_DEVICE float join_hf8(__half hi, uint8_t al8) { return fmaf(e5m2_to_f32(al8), 0.0009765625f, __half2float(hi)); }
+// byte offset of channel c's al8 inside a pixel's plane-1 row (its ah8 twin sits 64 bytes further)
+SHF_DEVICE int hf8_off(int c) { return ((c >> 6) << 7) + (c & 63); }
+
+// One element: px0 = plane-0 address of channel 0 of the pixel, plane_elems = elements per plane.
+SHF_DEVICE float act_load1(const __half* px0, size_t plane_elems, int c, int fmt) {
+  if (fmt == SHF_FMT_H2) return join_h2(px0[c], px0[plane_elems + c]);
+  return join_hf8(px0[c], reinterpret_cast<const uint8_t*>(px0 + plane_elems)[hf8_off(c)]);
+}
+SHF_DEVICE void act_store1(__half* px0, size_t plane_elems, int c, float v, int fmt) {
+  if (fmt == SHF_FMT_H2) {
+    __half hi, lo;
+    split_h2(v, hi, lo);
+    px0[c] = hi;
+    px0[plane_elems + c] = lo;
+  } else {
+    __half hi;
+    uint8_t a, b;
+    split_hf8(v, hi, a, b);
+    px0[c] = hi;
+    uint8_t* p1 = reinterpret_cast<uint8_t*>(px0 + plane_elems) + hf8_off(c);
+    p1[0] = a;
+    p1[64] = b;
+  }
+}
+// Eight consecutive channels c .. c+7 (c % 8 == 0): 16-byte vectors on plane 0 (and on plane 1 for h2), two 8-byte
+// vectors on plane 1 for hf8.
+SHF_DEVICE void act_load8(const __half* px0, size_t plane_elems, int c, float (&v)[8], int fmt) {
+  const uint4 vh = __ldg(reinterpret_cast<const uint4*>(px0 + c));
+  const __half2* hh = reinterpret_cast<const __half2*>(&vh);
+  if (fmt == SHF_FMT_H2) {
+    const uint4 vl = __ldg(reinterpret_cast<const uint4*>(px0 + plane_elems + c));
+    const __half2* ll = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(hh[j]), b = __half22float2(ll[j]);
+      v[2 * j] = a.x + b.x;
+      v[2 * j + 1] = a.y + b.y;
+    }
+  } else {
+    const uint2 va = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(px0 + plane_elems) + hf8_off(c)));
+    const uint8_t* ab = reinterpret_cast<const uint8_t*>(&va);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(hh[j]);
+      v[2 * j] = fmaf(e5m2_to_f32(ab[2 * j]), 0.0009765625f, a.x);
+      v[2 * j + 1] = fmaf(e5m2_to_f32(ab[2 * j + 1]), 0.0009765625f, a.y);
+    }
+  }
+}
+SHF_DEVICE void act_store8(__half* px0, size_t plane_elems, int c, const float (&v)[8], int fmt) {
+  uint32_t hp[4];
+  if (fmt == SHF_FMT_H2) {
+    uint32_t lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __half h0, l0, h1, l1;
+      split_h2(v[2 * e], h0, l0);
+      split_h2(v[2 * e + 1], h1, l1);
+      hp[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lp[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(px0 + c) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(px0 + plane_elems + c) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  } else {
+    uint32_t ap[2] = {0u, 0u}, bp[2] = {0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __half h0, h1;
+      uint8_t a0, b0, a1, b1;
+      split_hf8(v[2 * e], h0, a0, b0);
+      split_hf8(v[2 * e + 1], h1, a1, b1);
+      hp[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ap[e >> 1] |= ((uint32_t)a0 | ((uint32_t)a1 << 8)) << (16 * (e & 1));
+      bp[e >> 1] |= ((uint32_t)b0 | ((uint32_t)b1 << 8)) << (16 * (e & 1));
+    }
+    *reinterpret_cast<uint4*>(px0 + c) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    uint8_t* p1 = reinterpret_cast<uint8_t*>(px0 + plane_elems) + hf8_off(c);
+    *reinterpret_cast<uint2*>(p1) = make_uint2(ap[0], ap[1]);
+    *reinterpret_cast<uint2*>(p1 + 64) = make_uint2(bp[0], bp[1]);
+  }
+}
 
 // ----------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -212,7 +317,9 @@ SHF_DEVICE uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   return r;
 }
 SHF_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the only thing handed over is tensor memory, ordered by tcgen05.wait::ld + tcgen05.fence (a release here
+  // costs a MEMBAR per drain)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion bytes are credited to an mbarrier that may live in the peer CTA (cluster address)
 SHF_DEVICE void tma_load_5d_pair(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {

@@ -27,7 +27,7 @@ int shf_conv_pertap_impl(const void* in_h2, const void* w_h2, const float* bias,
 int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
-                         int ctas, void* stream);
+                         int ctas, int in_format, int out_format, void* stream);
 
 namespace {
 
@@ -290,11 +290,12 @@ int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 extern "C" int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, void* pool_out_h2,
                                    int batch, int H, int W, int cin, int cout, int ksize, int dilation,
                                    int out_channels_total, int out_channel_offset, int pool_channels_total,
-                                   int pool_channel_offset, float out_scale, int relu, void* stream) {
+                                   int pool_channel_offset, float out_scale, int relu, int in_format, int out_format,
+                                   void* stream) {
   SHF_REQUIRE(pool_out_h2 != nullptr, "shf_conv_igemm_pool: pool_out_h2 is NULL");
   return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                               out_channel_offset, out_scale, relu, pool_out_h2, pool_channels_total,
-                              pool_channel_offset, g_conv_impl == 7 ? 1 : 2, stream);
+                              pool_channel_offset, g_conv_impl == 7 ? 1 : 2, in_format, out_format, stream);
 }
 
 extern "C" int shf_set_conv_impl(int impl) {
@@ -306,10 +307,14 @@ extern "C" int shf_set_conv_impl(int impl) {
 // C ABI -- see include/shf_b200.h
 extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H,
                               int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
-                              int out_channel_offset, float out_scale, int relu, void* stream) {
+                              int out_channel_offset, float out_scale, int relu, int in_format, int out_format,
+                              void* stream) {
   if (g_conv_impl >= 7)
     return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
-                                out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_impl == 7 ? 1 : 2, stream);
+                                out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_impl == 7 ? 1 : 2, in_format,
+                                out_format, stream);
+  SHF_REQUIRE(in_format == SHF_FMT_H2 && out_format == SHF_FMT_H2,
+              "shf_conv_igemm: the v1/v2 kernels (shf_set_conv_impl < 7) only know the h2 format");
   if (g_conv_impl == 0)
     return shf_conv_pertap_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                                 out_channel_offset, out_scale, relu, stream);

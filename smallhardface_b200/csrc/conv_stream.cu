@@ -45,7 +45,7 @@ struct StreamParams {
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int chunks_per_phase;       // G
   int ctot, cout_offset, relu;
-  int probe;                  // timing probes (SHF_PROBE_MODE): 1 = two N=BN f16 MMAs per k-step, 2 = f16 + f8f6f4
+  int in_fmt, out_fmt;        // SHF_FMT_* of the input (and weight) planes / of the tensors written
   float out_scale;
   const float* bias;
   __half* out;                // h2 destination tensor base (plane 0); plane 1 at + plane_elems (nullptr: skip)
@@ -70,6 +70,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   // barriers: fullA[4] emptyA[4] fullB[6] emptyB[6] accFull[2] accEmpty[2]
   const uint32_t bar_base = smem_base + (uint32_t)pipe_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + 8 * (2 * kMaxA + 2 * kMaxB + 4));
+  float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 512);      // [2][BN]: this tile's bias slice, double-buffered
   auto full_a = [&](int s) { return bar_base + 8u * s; };
   auto empty_a = [&](int s) { return bar_base + 8u * (kMaxA + s); };
   auto full_b = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
@@ -165,7 +166,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== MMA issuer (warp converged, one elected lane issues; leader CTA only) =====================
     constexpr uint32_t idesc_wide = umma_idesc_f16(kTileM * CTAS, 2 * BN);     // A_hi x [B_hi ; B_lo]      (CTAS == 1)
     constexpr uint32_t idesc_half = umma_idesc_f16(kTileM * CTAS, BN);         // one operand-plane pair
-    constexpr uint32_t idesc_f8 = umma_idesc_f8(kTileM * CTAS, BN, 1u, 0u);    // timing probe only
+    constexpr uint32_t idesc_f8 = umma_idesc_f8(kTileM * CTAS, BN, 1u, 0u);    // A = e5m2 activations, B = e4m3 weights
     const uint32_t a_hi32 = (uint32_t)((p.xw * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
     constexpr uint32_t b_hi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t lbo = 1u << 16;
@@ -194,22 +195,32 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t a_off = (uint32_t)((r * p.dil) * p.xw + s * p.dil) * 128u;
             uint32_t a_lo32 = (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo;
             uint32_t b_lo32 = ((b_stage(sb) & 0x3FFFFu) >> 4) | lbo;
-            if (CTAS == 2) {
+            if (p.in_fmt == SHF_FMT_HF8) {
+              // hi*hi as one f16 MMA, the first-order correction [al8 | ah8] x [wh8 | wl8] as one f8 MMA over the
+              // same 32 bytes of K per operand row (plane 1 of either stage), both into the same accumulator
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) {
+                if (CTAS == 2) {
+                  umma_f16_pair_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+                  umma_f8_pair_elect_lohi(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+                } else {
+                  umma_f16_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+                  umma_f8_elect_lohi(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+                }
+                opened = 1u;
+                a_lo32 += 2; b_lo32 += 2;
+              }
+            } else if (CTAS == 2) {
               // the pair's weight stage is split by output channel, so hi and lo rows are separate N = BN operands:
               //   main += A_hi x B_hi ;  cross += A_hi x B_lo ;  cross += A_lo x B_hi
 #pragma unroll
               for (int k = 0; k < kChunkK / 16; ++k) {
                 umma_f16_pair_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                if (p.probe == 2) {
-                  umma_f8_pair_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, opened);
-                } else {
-                  umma_f16_pair_elect_lohi(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
-                  umma_f16_pair_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
-                }
+                umma_f16_pair_elect_lohi(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
+                umma_f16_pair_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
                 opened = 1u;
                 a_lo32 += 2; b_lo32 += 2;
               }
-              umma_commit_pair_elect(empty_b(sb));
             } else {
 #pragma unroll
               for (int k = 0; k < kChunkK / 16; ++k) {
@@ -220,8 +231,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 opened = 1u;
                 a_lo32 += 2; b_lo32 += 2;
               }
-              umma_commit_elect(empty_b(sb));
             }
+            if (CTAS == 2) umma_commit_pair_elect(empty_b(sb)); else umma_commit_elect(empty_b(sb));
             if (++s == ktaps) { s = 0; ++r; }
           }
           if (CTAS == 2) umma_commit_pair_elect(empty_a(sa)); else umma_commit_elect(empty_a(sa));
@@ -237,10 +248,16 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const float scale = p.out_scale;
     const uint32_t drained0 = (CTAS == 2) ? mapa_shared(acc_empty(0), 0) : acc_empty(0);   // in the leader
     const uint32_t drained1 = (CTAS == 2) ? mapa_shared(acc_empty(1), 0) : acc_empty(1);
-    int gp = 0;
+    int gp = 0, tile_it = 0;
     for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
       int nt, x0, y0, img;
       decode_tile(t, nt, x0, y0, img);
+      // stage this tile's bias slice in shared memory now, so that its global-load latency hides behind the main loop
+      // (read per 8-channel group straight from global memory it serialised ~16 L2 round trips into every epilogue)
+      float* bias_t = bias_s + (tile_it & 1) * BN;
+      if (m < BN) bias_t[m] = p.bias ? __ldg(p.bias + nt * BN + m) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+      ++tile_it;
       float acc[BN];
 #pragma unroll
       for (int c = 0; c < BN; ++c) acc[c] = 0.f;
@@ -249,15 +266,26 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_wait(acc_full(set), (gp >> 1) & 1);
         tc_fence_after();
         const uint32_t base = lane_addr + (uint32_t)set * kSetCols;
+        if (p.in_fmt == SHF_FMT_HF8) {
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t mq[32], cq[32];
-          tmem_ld_32x32(base + c0, mq);            // hi*hi partial
-          tmem_ld_32x32(base + BN + c0, cq);       // cross partial
-          tmem_ld_wait();
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t mq[32];
+            tmem_ld_32x32(base + c0, mq);            // hi*hi + correction partial
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            acc[c0 + e] = __fadd_rn(__fadd_rn(acc[c0 + e], __uint_as_float(cq[e])), __uint_as_float(mq[e]));
+            for (int e = 0; e < 32; ++e) acc[c0 + e] = __fadd_rn(acc[c0 + e], __uint_as_float(mq[e]));
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t mq[32], cq[32];
+            tmem_ld_32x32(base + c0, mq);            // hi*hi partial
+            tmem_ld_32x32(base + BN + c0, cq);       // cross partial
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              acc[c0 + e] = __fadd_rn(__fadd_rn(acc[c0 + e], __uint_as_float(cq[e])), __uint_as_float(mq[e]));
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -270,35 +298,22 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < p.H && x < p.W);
       const int n0 = nt * BN;
-      const float* bias = p.bias ? p.bias + n0 : nullptr;
-      __half* dst = p.out ? p.out + ((((size_t)img * p.H + y) * p.W + x) * (size_t)p.ctot + p.cout_offset + n0) : nullptr;
+      // plane-0 address of channel 0 of this thread's pixel (and of its pooled pixel)
+      __half* px0 = p.out ? p.out + (((size_t)img * p.H + y) * p.W + x) * (size_t)p.ctot : nullptr;
       const bool pool_writer = p.pool_out && inside && !(lane & 9);        // lane bits 0 (x) and 3 (y) clear: window origin
-      __half* pdst = p.pool_out ? p.pool_out + ((((size_t)img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
-                                                    (size_t)p.pool_ctot + p.pool_coffset + n0)
+      __half* ppx0 = p.pool_out ? p.pool_out + (((size_t)img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
+                                                   (size_t)p.pool_ctot
                                 : nullptr;
 #pragma unroll
       for (int c = 0; c < BN; c += 8) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          v[e] = acc[c + e] * scale + (bias ? __ldg(bias + c + e) : 0.f);
+          v[e] = fmaf(acc[c + e], scale, bias_t[c + e]);
           if (p.relu) v[e] = fmaxf(v[e], 0.f);
         }
-        if (dst && inside) {
-          uint32_t hi_pk[4], lo_pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half h0, l0, h1, l1;
-            split_h2(v[2 * e], h0, l0);
-            split_h2(v[2 * e + 1], h1, l1);
-            hi_pk[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo_pk[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-          }
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(hi_pk[0], hi_pk[1], hi_pk[2], hi_pk[3]);
-          *reinterpret_cast<uint4*>(dst + p.plane_elems + c) = make_uint4(lo_pk[0], lo_pk[1], lo_pk[2], lo_pk[3]);
-        }
+        if (px0 && inside) act_store8(px0, (size_t)p.plane_elems, p.cout_offset + n0 + c, v, p.out_fmt);
         if (p.pool_out) {                                   // warp-uniform branch: all lanes take part in the shuffles
-          uint32_t hi_pk[4], lo_pk[4];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             float q = inside ? v[e] : -3.402823466e38f;
@@ -306,18 +321,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
             v[e] = q;
           }
-          if (pool_writer) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __half h0, l0, h1, l1;
-              split_h2(v[2 * e], h0, l0);
-              split_h2(v[2 * e + 1], h1, l1);
-              hi_pk[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              lo_pk[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-            }
-            *reinterpret_cast<uint4*>(pdst + c) = make_uint4(hi_pk[0], hi_pk[1], hi_pk[2], hi_pk[3]);
-            *reinterpret_cast<uint4*>(pdst + p.pool_plane_elems + c) = make_uint4(lo_pk[0], lo_pk[1], lo_pk[2], lo_pk[3]);
-          }
+          if (pool_writer) act_store8(ppx0, (size_t)p.pool_plane_elems, p.pool_coffset + n0 + c, v, p.out_fmt);
         }
       }
     }
@@ -375,8 +379,14 @@ int sm_count() {
 int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
-                         int ctas, void* stream) {
+                         int ctas, int in_format, int out_format, void* stream) {
   SHF_REQUIRE(ctas == 1 || ctas == 2, "shf_conv_igemm: %d CTAs per tile group", ctas);
+  SHF_REQUIRE((in_format == SHF_FMT_H2 || in_format == SHF_FMT_HF8) && (out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8),
+              "shf_conv_igemm: unknown activation format %d / %d", in_format, out_format);
+  if (out_format == SHF_FMT_HF8)
+    SHF_REQUIRE(out_channel_offset % 64 == 0 && out_channels_total % 64 == 0 &&
+                    (!pool_out_h2 || (pool_channel_offset % 64 == 0 && pool_channels_total % 64 == 0)),
+                "shf_conv_igemm: hf8 tensors need channel windows aligned to 64");
   SHF_REQUIRE(out_h2 != nullptr || pool_out_h2 != nullptr, "shf_conv_igemm: no destination");
   if (pool_out_h2)
     SHF_REQUIRE(H % 2 == 0 && W % 2 == 0 && pool_channel_offset % 8 == 0 && pool_channels_total % 8 == 0 &&
@@ -402,7 +412,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.a_tx = 2 * p.xh * p.xw * 128;
   p.a_bytes = (p.a_tx + 1023) & ~1023;
   p.b_bytes = 2 * (bn / ctas) * 128;          // per CTA: its share of the output channels, hi + lo plane
-  const int budget = 227 * 1024 - 1024 - 512;
+  const int budget = 227 * 1024 - 1024 - 1536;      // alignment slack; barriers (512) + staged bias (1024)
   p.na = (p.taps == 1) ? kMaxA : 2;
   while (p.na > 1 && p.na * p.a_bytes + 3 * p.b_bytes > budget) --p.na;
   p.nb = (budget - p.na * p.a_bytes) / p.b_bytes;
@@ -418,8 +428,8 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.ctot = out_channels_total;
   p.cout_offset = out_channel_offset;
   p.relu = relu;
-  p.probe = 0;
-  if (const char* e = getenv("SHF_PROBE_MODE")) p.probe = atoi(e);
+  p.in_fmt = in_format;
+  p.out_fmt = out_format;
   p.out_scale = out_scale;
   p.bias = bias;
   p.out = reinterpret_cast<__half*>(out_h2);
@@ -428,7 +438,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.pool_plane_elems = (long long)batch * (H / 2) * (W / 2) * pool_channels_total;
   p.pool_ctot = pool_channels_total;
   p.pool_coffset = pool_channel_offset;
-  const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 512;
+  const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 1536;
 
   CUtensorMap ta, tb;
   {

@@ -1,7 +1,7 @@
 // HBM-bound layers of the deploy nets as plain SIMT kernels (sm_100a): the 3-channel first conv,
 // 2x2 max pooling, the depthwise 2x bilinear deconvolution, layout/precision converters, the image
 // pyramid pre-processing, and a slow direct convolution used only to validate the tcgen05 kernel.
-// Activations are NHWC split-fp16 ("h2": planes [2][N][H][W][C], x = hi + lo), see common.cuh.
+// Activations are NHWC in one of the two 4-byte formats of common.cuh (h2 = split fp16, hf8 = fp16 + 8-bit floats).
 #include "common.cuh"
 
 namespace {
@@ -31,7 +31,7 @@ SHF_DEVICE uint4 pack8(const __half (&h)[8]) {
 template <int COUT>
 __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                          const float* __restrict__ bias, __half* __restrict__ out,
-                                                         int N, int H, int W, int relu) {
+                                                         int N, int H, int W, int relu, int out_fmt) {
   // Work split chosen for the STORE side (this layer writes 256 B per pixel and reads 12): four lanes share a run of
   // four horizontally adjacent pixels, each lane owning 16 of the 64 output channels.  A quad therefore writes each
   // pixel's 128-byte hi row (and lo row) as one full cache line, and one warp-wide store instruction covers 8 lines.
@@ -95,19 +95,16 @@ __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       if (x + px >= W) break;
-      __half* ohi = out + (pix0 + px) * COUT + part * 16;
-      __half* olo = ohi + plane;
+      __half* opx = out + (pix0 + px) * COUT;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        __half hi[8], lo[8];
+        float t[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float t0 = acc[px][h * 8 + j] + bs[part * 16 + h * 8 + j];
-          if (relu) t0 = fmaxf(t0, 0.f);
-          split_h2(t0, hi[j], lo[j]);
+          t[j] = acc[px][h * 8 + j] + bs[part * 16 + h * 8 + j];
+          if (relu) t[j] = fmaxf(t[j], 0.f);
         }
-        *reinterpret_cast<uint4*>(ohi + h * 8) = pack8(hi);
-        *reinterpret_cast<uint4*>(olo + h * 8) = pack8(lo);
+        act_store8(opx, plane, part * 16 + h * 8, t, out_fmt);
       }
     }
   }
@@ -118,7 +115,7 @@ __global__ void __launch_bounds__(128) conv3x3_c3_kernel(const float* __restrict
 // ceil-mode output size).  One thread = one output pixel x 8 channels (16-byte vectors per plane).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool2x2_h2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
-                                                            int N, int H, int W, int C, int HO, int WO) {
+                                                            int N, int H, int W, int C, int HO, int WO, int fmt) {
   const int cv = C / 8;
   const long long total = (long long)N * HO * WO * cv;
   const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * C;
@@ -129,31 +126,21 @@ __global__ void __launch_bounds__(256) maxpool2x2_h2_kernel(const __half* __rest
     const int oy = (int)((i / ((long long)cv * WO)) % HO);
     const int n = (int)(i / ((long long)cv * WO * HO));
     float best[8];
-    __half bh[8], bl[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -3.402823466e38f; bh[j] = __float2half(0.f); bl[j] = __float2half(0.f); }
+    for (int j = 0; j < 8; ++j) best[j] = -3.402823466e38f;
     for (int dy = 0; dy < 2; ++dy) {
       const int iy = oy * 2 + dy;
       if (iy >= H) continue;
       for (int dx = 0; dx < 2; ++dx) {
         const int ix = ox * 2 + dx;
         if (ix >= W) continue;
-        const size_t off = (((size_t)n * H + iy) * W + ix) * C + (size_t)c8 * 8;
-        const uint4 vh = __ldg(reinterpret_cast<const uint4*>(in + off));
-        const uint4 vl = __ldg(reinterpret_cast<const uint4*>(in + in_plane + off));
-        __half h[8], l[8];
-        unpack8(vh, h);
-        unpack8(vl, l);
+        float v[8];
+        act_load8(in + (((size_t)n * H + iy) * W + ix) * C, in_plane, c8 * 8, v, fmt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = join_h2(h[j], l[j]);
-          if (v > best[j]) { best[j] = v; bh[j] = h[j]; bl[j] = l[j]; }      // first maximum wins, strict >
-        }
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], v[j]);      // re-splitting the maximum reproduces its planes
       }
     }
-    const size_t o = (((size_t)n * HO + oy) * WO + ox) * C + (size_t)c8 * 8;
-    *reinterpret_cast<uint4*>(out + o) = pack8(bh);
-    *reinterpret_cast<uint4*>(out + out_plane + o) = pack8(bl);
+    act_store8(out + (((size_t)n * HO + oy) * WO + ox) * C, out_plane, c8 * 8, best, fmt);
   }
 }
 
@@ -164,7 +151,8 @@ __global__ void __launch_bounds__(256) maxpool2x2_h2_kernel(const __half* __rest
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                            __half* __restrict__ out, int N, int H, int W, int C,
-                                                           int K, int S, int P, int HO, int WO, int CT, int c_off) {
+                                                           int K, int S, int P, int HO, int WO, int CT, int c_off,
+                                                           int in_fmt, int out_fmt) {
   const int cv = C / 8;
   const long long total = (long long)N * HO * WO * cv;
   const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * CT;
@@ -187,21 +175,13 @@ __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restr
         if (tx < 0 || tx % S) continue;
         const int ix = tx / S;
         if (ix >= W) continue;
-        const size_t off = (((size_t)n * H + iy) * W + ix) * C + (size_t)c8 * 8;
-        __half h[8], l[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(in + off)), h);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(in + in_plane + off)), l);
+        float v[8];
+        act_load8(in + (((size_t)n * H + iy) * W + ix) * C, in_plane, c8 * 8, v, in_fmt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          acc[j] += join_h2(h[j], l[j]) * __ldg(w + ((size_t)(c8 * 8 + j) * K + ky) * K + kx);
+        for (int j = 0; j < 8; ++j) acc[j] += v[j] * __ldg(w + ((size_t)(c8 * 8 + j) * K + ky) * K + kx);
       }
     }
-    __half hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) split_h2(acc[j], hi[j], lo[j]);
-    const size_t o = (((size_t)n * HO + oy) * WO + ox) * CT + c_off + (size_t)c8 * 8;
-    *reinterpret_cast<uint4*>(out + o) = pack8(hi);
-    *reinterpret_cast<uint4*>(out + out_plane + o) = pack8(lo);
+    act_store8(out + (((size_t)n * HO + oy) * WO + ox) * CT, out_plane, c_off + c8 * 8, acc, out_fmt);
   }
 }
 
@@ -211,7 +191,7 @@ __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restr
 // (ky ascending, then kx ascending) is the same as the generic kernel / col2im.
 __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                                __half* __restrict__ out, int N, int H, int W, int C,
-                                                               int CT, int c_off) {
+                                                               int CT, int c_off, int in_fmt, int out_fmt) {
   extern __shared__ float wsm[];                 // [C][16]
   for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
@@ -238,20 +218,13 @@ __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __r
         const int kx = kx0 + 2 * b;
         const int ix = (ox + 1 - kx) >> 1;
         if (ox + 1 - kx < 0 || ix >= W) continue;
-        const size_t off = (((size_t)n * H + iy) * W + ix) * C + (size_t)c8 * 8;
-        __half h[8], l[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(in + off)), h);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(in + in_plane + off)), l);
+        float v[8];
+        act_load8(in + (((size_t)n * H + iy) * W + ix) * C, in_plane, c8 * 8, v, in_fmt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += join_h2(h[j], l[j]) * wsm[(c8 * 8 + j) * 16 + ky * 4 + kx];
+        for (int j = 0; j < 8; ++j) acc[j] += v[j] * wsm[(c8 * 8 + j) * 16 + ky * 4 + kx];
       }
     }
-    __half hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) split_h2(acc[j], hi[j], lo[j]);
-    const size_t o = (((size_t)n * HO + oy) * WO + ox) * CT + c_off + (size_t)c8 * 8;
-    *reinterpret_cast<uint4*>(out + o) = pack8(hi);
-    *reinterpret_cast<uint4*>(out + out_plane + o) = pack8(lo);
+    act_store8(out + (((size_t)n * HO + oy) * WO + ox) * CT, out_plane, c_off + c8 * 8, acc, out_fmt);
   }
 }
 
@@ -259,7 +232,7 @@ __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __r
 // Layout / precision converters (the Blob.data boundary: Caffe blobs are fp32 NCHW)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) h2_to_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int N,
-                                                         int H, int W, int CT, int c_off, int C) {
+                                                         int H, int W, int CT, int c_off, int C, int fmt) {
   // one thread per (n, y, x, c): reads are channel-contiguous; a 32x32 smem transpose would make both
   // sides coalesced, but this only runs when a host reads an intermediate blob (debug / parity tests)
   const long long total = (long long)N * H * W * C;
@@ -271,13 +244,12 @@ __global__ void __launch_bounds__(256) h2_to_nchw_kernel(const __half* __restric
     const int x = (int)(pix % W);
     const int y = (int)((pix / W) % H);
     const int n = (int)(pix / ((long long)W * H));
-    const size_t src = (size_t)pix * CT + c_off + c;
-    out[(((size_t)n * C + c) * H + y) * W + x] = join_h2(in[src], in[plane + src]);
+    out[(((size_t)n * C + c) * H + y) * W + x] = act_load1(in + (size_t)pix * CT, plane, c_off + c, fmt);
   }
 }
 
 __global__ void __launch_bounds__(256) nchw_to_h2_kernel(const float* __restrict__ in, __half* __restrict__ out, int N,
-                                                         int C, int H, int W, int CT, int c_off) {
+                                                         int C, int H, int W, int CT, int c_off, int fmt) {
   const long long total = (long long)N * H * W * C;
   const size_t plane = (size_t)N * H * W * CT;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -287,11 +259,7 @@ __global__ void __launch_bounds__(256) nchw_to_h2_kernel(const float* __restrict
     const int x = (int)(pix % W);
     const int y = (int)((pix / W) % H);
     const int n = (int)(pix / ((long long)W * H));
-    __half hi, lo;
-    split_h2(in[(((size_t)n * C + c) * H + y) * W + x], hi, lo);
-    const size_t dst = (size_t)pix * CT + c_off + c;
-    out[dst] = hi;
-    out[plane + dst] = lo;
+    act_store1(out + (size_t)pix * CT, plane, c_off + c, in[(((size_t)n * C + c) * H + y) * W + x], fmt);
   }
 }
 
@@ -356,7 +324,8 @@ __global__ void __launch_bounds__(256) preprocess_level_kernel(const uint8_t* __
 __global__ void __launch_bounds__(256) conv_direct_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ bias, __half* __restrict__ out,
                                                              int N, int H, int W, int CI, int CO, int K, int dil,
-                                                             int pad, int CT, int c_off, int relu) {
+                                                             int pad, int CT, int c_off, int relu, int in_fmt,
+                                                             int out_fmt) {
   const long long total = (long long)N * H * W * CO;
   const size_t in_plane = (size_t)N * H * W * CI, out_plane = (size_t)N * H * W * CT;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -375,16 +344,12 @@ __global__ void __launch_bounds__(256) conv_direct_h2_kernel(const __half* __res
         if (ix < 0 || ix >= W) continue;
         const __half* ph = in + (((size_t)n * H + iy) * W + ix) * CI;
         const float* pw = w + ((size_t)o * CI * K + r) * K + s;          // OIHW
-        for (int c = 0; c < CI; ++c) acc = fmaf(join_h2(ph[c], ph[in_plane + c]), pw[(size_t)c * K * K], acc);
+        for (int c = 0; c < CI; ++c) acc = fmaf(act_load1(ph, in_plane, c, in_fmt), pw[(size_t)c * K * K], acc);
       }
     }
     acc += bias ? bias[o] : 0.f;
     if (relu) acc = fmaxf(acc, 0.f);
-    __half hi, lo;
-    split_h2(acc, hi, lo);
-    const size_t dst = (size_t)pix * CT + c_off + o;
-    out[dst] = hi;
-    out[out_plane + dst] = lo;
+    act_store1(out + (size_t)pix * CT, out_plane, c_off + o, acc, out_fmt);
   }
 }
 
@@ -397,59 +362,68 @@ int grid_for(long long total, int block) {
 }  // namespace
 
 extern "C" int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch,
-                            int H, int W, int cout, int relu, void* stream) {
+                            int H, int W, int cout, int relu, int out_format, void* stream) {
+  SHF_REQUIRE(out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8, "shf_conv1_c3: unknown activation format %d", out_format);
   SHF_REQUIRE(cout == 64, "shf_conv1_c3: Cout=%d (the deploy nets' conv1_1 has 64)", cout);
   const long long npix = (long long)batch * H * ((W + 3) / 4) * 4;  // four threads per run of four pixels
   conv3x3_c3_kernel<64><<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(in_nchw, w_oihw, bias, (__half*)out_h2,
-                                                                               batch, H, W, relu);
+                                                                               batch, H, W, relu, out_format);
   SHF_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, void* stream) {
+extern "C" int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, int format, void* stream) {
   SHF_REQUIRE(C % 8 == 0, "shf_maxpool2x2: C=%d must be a multiple of 8", C);
+  SHF_REQUIRE(format == SHF_FMT_H2 || (format == SHF_FMT_HF8 && C % 64 == 0), "shf_maxpool2x2: format %d with C=%d", format, C);
   const int HO = (H + 1) / 2, WO = (W + 1) / 2;       // ceil mode, pooling_layer.cpp:91-94 with k=s=2, pad 0
   const long long total = (long long)batch * HO * WO * (C / 8);
   maxpool2x2_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)in_h2, (__half*)out_h2,
-                                                                             batch, H, W, C, HO, WO);
+                                                                             batch, H, W, C, HO, WO, format);
   SHF_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int shf_deconv_depthwise(const void* in_h2, const float* w, void* out_h2, int batch, int H, int W, int C,
                                     int ksize, int stride, int pad, int out_channels_total, int out_channel_offset,
-                                    void* stream) {
+                                    int in_format, int out_format, void* stream) {
   SHF_REQUIRE(C % 8 == 0 && out_channel_offset % 8 == 0 && out_channels_total % 8 == 0,
               "shf_deconv_depthwise: channel counts must be multiples of 8");
+  SHF_REQUIRE((in_format == SHF_FMT_H2 || (in_format == SHF_FMT_HF8 && C % 64 == 0)) &&
+                  (out_format == SHF_FMT_H2 ||
+                   (out_format == SHF_FMT_HF8 && out_channel_offset % 64 == 0 && out_channels_total % 64 == 0 && C % 64 == 0)),
+              "shf_deconv_depthwise: formats %d/%d need 64-aligned channel windows for hf8", in_format, out_format);
   const int HO = stride * (H - 1) + ksize - 2 * pad, WO = stride * (W - 1) + ksize - 2 * pad;   // deconv_layer.cpp:8-28
   const long long total = (long long)batch * HO * WO * (C / 8);
   if (ksize == 4 && stride == 2 && pad == 1 && C * 16 * sizeof(float) <= 48 * 1024) {
     deconv_k4s2p1_h2_kernel<<<grid_for(total, 256), 256, C * 16 * sizeof(float), (cudaStream_t)stream>>>(
-        (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, out_channels_total, out_channel_offset);
+        (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, out_channels_total, out_channel_offset, in_format,
+        out_format);
     SHF_LAUNCH_CHECK();
     return 0;
   }
   deconv_dw_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, ksize, stride, pad, HO, WO, out_channels_total,
-      out_channel_offset);
+      out_channel_offset, in_format, out_format);
   SHF_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int shf_h2_to_nchw(const void* in_h2, float* out_nchw, int batch, int H, int W, int channels_total,
-                              int channel_offset, int channels, void* stream) {
+                              int channel_offset, int channels, int format, void* stream) {
+  SHF_REQUIRE(format == SHF_FMT_H2 || (format == SHF_FMT_HF8 && channels_total % 64 == 0), "shf_h2_to_nchw: format %d", format);
   const long long total = (long long)batch * H * W * channels;
   h2_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)in_h2, out_nchw, batch, H, W,
-                                                                          channels_total, channel_offset, channels);
+                                                                          channels_total, channel_offset, channels, format);
   SHF_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int shf_nchw_to_h2(const float* in_nchw, void* out_h2, int batch, int channels, int H, int W,
-                              int channels_total, int channel_offset, void* stream) {
+                              int channels_total, int channel_offset, int format, void* stream) {
+  SHF_REQUIRE(format == SHF_FMT_H2 || (format == SHF_FMT_HF8 && channels_total % 64 == 0), "shf_nchw_to_h2: format %d", format);
   const long long total = (long long)batch * H * W * channels;
   nchw_to_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in_nchw, (__half*)out_h2, batch, channels, H,
-                                                                          W, channels_total, channel_offset);
+                                                                          W, channels_total, channel_offset, format);
   SHF_LAUNCH_CHECK();
   return 0;
 }
@@ -468,11 +442,12 @@ extern "C" int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float*
 
 extern "C" int shf_debug_conv_direct(const void* in_h2, const float* w_oihw, const float* bias, void* out_h2, int batch,
                                      int H, int W, int cin, int cout, int ksize, int dilation, int pad,
-                                     int out_channels_total, int out_channel_offset, int relu, void* stream) {
+                                     int out_channels_total, int out_channel_offset, int relu, int in_format,
+                                     int out_format, void* stream) {
   const long long total = (long long)batch * H * W * cout;
   conv_direct_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)in_h2, w_oihw, bias, (__half*)out_h2, batch, H, W, cin, cout, ksize, dilation, pad,
-      out_channels_total, out_channel_offset, relu);
+      out_channels_total, out_channel_offset, relu, in_format, out_format);
   SHF_LAUNCH_CHECK();
   return 0;
 }

@@ -40,6 +40,9 @@ class DetectConfig:
     pixel_means: Sequence[float] = (102.9801, 115.9465, 122.7717)   # PIXEL_MEANS
     nms_mode: int = 0                                          # 0 = cpu_nms (>=), 1 = gpu_nms (>)
     max_dets_out: int = 4096                                   # rows returned per image (post vote / NMS)
+    # not a reference key: pyramid levels with im_scale >= this run the convs on the fast f16+f8 operand format, smaller
+    # (error-magnifying) levels on precise split fp16; None = precise everywhere (see GpuNet / tools/precision_model.py)
+    fast_min_scale: float | None = 0.5
 
 
 def compute_scaling_factor(im_shape, target_size, max_size):
@@ -75,7 +78,8 @@ class Detector:
         spec = NetSpec(net_param, TEST)
         params = load_weights(spec, model)
         self.net = GpuNet(spec, params, device, pre_nms_topn=self.cfg.n_dets_per_module,
-                          score_thresh=self.cfg.score_thresh, min_size=self.cfg.anchor_min_size)
+                          score_thresh=self.cfg.score_thresh, min_size=self.cfg.anchor_min_size,
+                          fast_min_scale=self.cfg.fast_min_scale)
         self._means = (C.c_double * 3)(*self.cfg.pixel_means)
         self._bufs = {}
         self.max_batch_bytes = 40e9          # activation budget used to size per-level batches (180 GB HBM per GPU)
@@ -158,7 +162,7 @@ class Detector:
                 for c0 in range(0, len(idxs), chunk):
                     sub = idxs[c0:c0 + chunk]
                     data, info = self._level_batch([dev_images[i] for i in sub], s, flips)
-                    self.net.forward_body(data)
+                    self.net.forward_body(data, fast=self.net.use_fast(s))
                     self.net.run_tail_batched(nf, info, b["dets"], b["offs"], image_base=sub[0], passes_total=passes,
                                               pass_base=li * nf, det_cap=b["cap"], det_thresh=cfg.thresh)
         torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])

@@ -66,16 +66,48 @@ def pack_conv_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
     return np.stack([lay(hi), lay(lo)]), k
 
 
+def pack_conv_weights_hf8(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
+    """The same tensor for the fast ("hf8") operand format: plane 0 = hi = rn_f16(w * 2^k) as above; plane 1 holds,
+    per (tap, Cout, block of 64 input channels), 64 bytes e4m3(hi * 2^-10) followed by 64 bytes e4m3(lo) -- the
+    8-bit twin of the activation plane [e5m2(lo_x * 2^10) | e5m2(hi_x)], so that one K = 128 row pair contracts to
+    lo_x * hi_w + hi_x * lo_w at the scale 2^k of the main product.  Returned as float16-typed storage."""
+    w = np.asarray(w_oihw, dtype=np.float32)
+    co, ci, kh, kw = w.shape
+    if ci % 64:
+        raise ValueError("hf8 weights need Cin % 64 == 0")
+    amax = float(np.abs(w).max())
+    k = 0 if amax == 0 or not np.isfinite(amax) else int(14 - math.ceil(math.log2(amax)))
+    k = max(-14, min(k, 24))
+    ws = w * np.float32(2.0 ** k)
+    hi = ws.astype(np.float16)
+    lo = ws - hi.astype(np.float32)
+    def e4m3(a):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).clamp_(-448.0, 448.0)
+        return t.to(torch.float8_e4m3fn).view(torch.uint8).numpy()
+    def lay(a):
+        return np.ascontiguousarray(a.transpose(2, 3, 0, 1).reshape(kh * kw, co, ci))
+    hi_l = lay(hi)
+    wh8 = e4m3(lay(hi.astype(np.float32) * np.float32(2.0 ** -10))).reshape(kh * kw, co, ci // 64, 1, 64)
+    wl8 = e4m3(lay(lo)).reshape(kh * kw, co, ci // 64, 1, 64)
+    plane1 = np.ascontiguousarray(np.concatenate([wh8, wl8], axis=3)).reshape(kh * kw, co, ci * 2)
+    return np.stack([hi_l, plane1.view(np.float16)]), k
+
+
+FMT_H2, FMT_HF8 = L.FMT_H2, L.FMT_HF8
+
+
 class H2:
-    """NHWC split-fp16 activation tensor: torch.float16 (2, N, H, W, C), optionally a channel window
+    """NHWC activation tensor in one of the two 4-byte formats of include/shf_b200.h (``fmt``): torch.float16
+    storage (2, N, H, W, C) -- for hf8 plane 1 is really bytes --, optionally a channel window
     [c_off, c_off + C) of a wider tensor (how Concat is realised)."""
 
-    __slots__ = ("t", "c_off", "c")
+    __slots__ = ("t", "c_off", "c", "fmt")
 
-    def __init__(self, t: torch.Tensor, c_off: int = 0, c: Optional[int] = None):
+    def __init__(self, t: torch.Tensor, c_off: int = 0, c: Optional[int] = None, fmt: int = FMT_H2):
         self.t = t
         self.c_off = c_off
         self.c = t.shape[4] if c is None else c
+        self.fmt = fmt
 
     @property
     def n(self): return self.t.shape[1]
@@ -87,20 +119,21 @@ class H2:
     def ctot(self): return self.t.shape[4]
 
     @staticmethod
-    def empty(n, h, w, c, device):
-        return H2(torch.empty((2, n, h, w, c), dtype=torch.float16, device=device))
+    def empty(n, h, w, c, device, fmt: int = FMT_H2):
+        return H2(torch.empty((2, n, h, w, c), dtype=torch.float16, device=device), fmt=fmt)
 
     def to_nchw(self) -> torch.Tensor:
         out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.t.device)
-        L.call("shf_h2_to_nchw", _ptr(self.t), _ptr(out), self.n, self.h, self.w, self.ctot, self.c_off, self.c, _stream())
+        L.call("shf_h2_to_nchw", _ptr(self.t), _ptr(out), self.n, self.h, self.w, self.ctot, self.c_off, self.c,
+               self.fmt, _stream())
         return out
 
     @staticmethod
-    def from_nchw(x: torch.Tensor) -> "H2":
+    def from_nchw(x: torch.Tensor, fmt: int = FMT_H2) -> "H2":
         x = x.contiguous().float()
         n, c, h, w = x.shape
-        out = H2.empty(n, h, w, c, x.device)
-        L.call("shf_nchw_to_h2", _ptr(x), _ptr(out.t), n, c, h, w, c, 0, _stream())
+        out = H2.empty(n, h, w, c, x.device, fmt)
+        L.call("shf_nchw_to_h2", _ptr(x), _ptr(out.t), n, c, h, w, c, 0, fmt, _stream())
         return out
 
 
@@ -119,10 +152,16 @@ class GpuNet:
     the device plus ``im_info`` and leaves every materialised blob in ``self.tensors``."""
 
     def __init__(self, spec: NetSpec, params: Dict[str, np.ndarray], device="cuda:0", pre_nms_topn=10000,
-                 score_thresh=0.002, min_size=0.0, fuse_pool=True):
+                 score_thresh=0.002, min_size=0.0, fuse_pool=True, fast_min_scale=0.5):
         """``fuse_pool``: run Convolution+ReLU+Pooling(MAX 2x2/2) as one launch; the un-pooled conv blob is then
-        only materialised if something else consumes it (pass False to be able to read every blob)."""
+        only materialised if something else consumes it (pass False to be able to read every blob).
+
+        ``fast_min_scale``: pyramid levels whose ``im_info`` scale is at least this run the convolutions on the fast
+        hf8 operand format (1 fp16 + 1 fp8 MMA per 16 channels, ~2^-15 operands); smaller levels -- whose box errors
+        are MAGNIFIED by 1/scale when mapped back to the raw image (``lib/test.py:62``) -- keep the precise split-fp16
+        format (3 fp16 MMAs, 2^-22).  ``None`` disables the fast format.  tools/precision_model.py has the numbers."""
         L.load()
+        self.fast_min_scale = fast_min_scale
         import os
         self.fuse_pool = bool(fuse_pool) and not os.environ.get("SHF_MATERIALIZE_ALL")
         self.spec = spec
@@ -212,6 +251,10 @@ class GpuNet:
                     packed, k = pack_conv_weights(w)
                     st["w"] = torch.from_numpy(packed).to(dev)
                     st["scale"] = float(2.0 ** (-k))
+                    if self.fast_min_scale is not None:
+                        packed8, k8 = pack_conv_weights_hf8(w)
+                        assert k8 == k
+                        st["w8"] = torch.from_numpy(packed8).to(dev)
                     nxt = i + (2 if relu else 1)
                     pl = layers[nxt] if nxt < len(layers) else None
                     if (self.fuse_pool and pl is not None and pl.type == "Pooling" and pl.bottoms == l.tops
@@ -312,32 +355,42 @@ class GpuNet:
                     cls_blob=cls_blob, box_blob=box_blob, fused=[l.name for l in chain])
 
     # -- execution -------------------------------------------------------------------------------------
-    def _alloc_out(self, blob: str, n, h, w, c) -> H2:
+    def _alloc_out(self, blob: str, n, h, w, c, fmt: int = FMT_H2) -> H2:
+        if self.tail is not None and blob in self.tail["feats"]:
+            fmt = FMT_H2                              # the detection-tail kernel reads split fp16 (and gains its precision)
         if blob in self.concat_dst:
             top, off, total = self.concat_dst[blob]
             dst = self.tensors.get(top)
-            if dst is None or (dst.n, dst.h, dst.w, dst.ctot) != (n, h, w, total):
-                dst = H2.empty(n, h, w, total, self.device)
+            if dst is None or (dst.n, dst.h, dst.w, dst.ctot, dst.fmt) != (n, h, w, total, fmt):
+                dst = H2.empty(n, h, w, total, self.device, fmt)
                 self.tensors[top] = dst
-            out = H2(dst.t, off, c)
+            out = H2(dst.t, off, c, fmt)
         else:
-            out = H2.empty(n, h, w, c, self.device)
+            out = H2.empty(n, h, w, c, self.device, fmt)
         self.tensors[blob] = out
         return out
+
+    def use_fast(self, im_scale) -> bool:
+        """Operand-format policy for one pyramid level (see ``fast_min_scale``)."""
+        return self.fast_min_scale is not None and im_scale is not None and float(im_scale) >= self.fast_min_scale
 
     def forward(self, data: torch.Tensor, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False,
                 det_thresh=0.05):
         """data: (1,3,H,W) fp32 on the device.  im_info: (h, w, scale) of the unpadded level.
         Returns (boxes (topn,5), probs (topn,2), rows (1,) int32) device tensors; when ``dets`` is given the
         pass is also appended to the image-level detection list (see shf_proposal_gather)."""
-        self.forward_body(data)
+        self.forward_body(data, fast=self.use_fast(im_info[2]))
         if self.tail is None:
             return None
         return self.run_tail(0, im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh)
 
-    def forward_body(self, data: torch.Tensor):
+    def forward_body(self, data: torch.Tensor, fast: bool = False):
         """Runs every layer up to the detection tail on a batch (N,3,H,W); blobs stay on the device in
-        ``self.tensors``.  The ProposalLayer is per image (``proposal_layer.py:74-75``): call ``run_tail(n, ...)``."""
+        ``self.tensors``.  The ProposalLayer is per image (``proposal_layer.py:74-75``): call ``run_tail(n, ...)``.
+        ``fast``: activations (and conv operands) in the hf8 format instead of split fp16."""
+        if fast and self.fast_min_scale is None:
+            raise L.ShfError("this GpuNet was built without the fast operand format (fast_min_scale=None)")
+        fmt = FMT_HF8 if fast else FMT_H2
         T = self.tensors
         T.clear()
         T["data"] = data
@@ -350,45 +403,52 @@ class GpuNet:
             x = T[l.bottoms[0]]
             if kind == "conv1":
                 n, _, h, w = x.shape
-                out = self._alloc_out(l.tops[0], n, h, w, s["cout"])
+                out = self._alloc_out(l.tops[0], n, h, w, s["cout"], fmt)
                 L.call("shf_conv1_c3", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
-                       int(s["relu"]), st)
+                       int(s["relu"]), out.fmt, st)
             elif kind == "conv":
                 if x.c_off != 0 or x.c != x.ctot:
                     raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
                 fused = "pool_top" in s and x.h % 2 == 0 and x.w % 2 == 0
                 out = None
+                wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
                 if not fused or s["write_full"]:
-                    out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"])
+                    out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"], fmt)
                 if self.profile:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()
                 if fused:
-                    pooled = self._alloc_out(s["pool_top"], x.n, x.h // 2, x.w // 2, s["cout"])
-                    L.call("shf_conv_igemm_pool", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t if out else None),
+                    pooled = self._alloc_out(s["pool_top"], x.n, x.h // 2, x.w // 2, s["cout"], fmt)
+                    if out is not None and out.fmt != pooled.fmt:
+                        raise L.ShfError("conv %s: full and pooled outputs need one format" % l.name)
+                    L.call("shf_conv_igemm_pool", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t if out else None),
                            _ptr(pooled.t), x.n, x.h, x.w, s["cin"], s["cout"], s["k"], s["dil"],
                            out.ctot if out else s["cout"], out.c_off if out else 0, pooled.ctot, pooled.c_off,
-                           s["scale"], int(s["relu"]), st)
+                           s["scale"], int(s["relu"]), x.fmt, pooled.fmt, st)
                 else:
-                    L.call("shf_conv_igemm", _ptr(x.t), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
-                           s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), st)
+                    L.call("shf_conv_igemm", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
+                           s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, st)
                     if "pool_top" in s:                      # odd size: pooling could not be fused
-                        pooled = self._alloc_out(s["pool_top"], x.n, (x.h + 1) // 2, (x.w + 1) // 2, s["cout"])
-                        L.call("shf_maxpool2x2", _ptr(out.t), _ptr(pooled.t), x.n, x.h, x.w, s["cout"], st)
+                        if out.c_off != 0 or out.c != out.ctot:
+                            raise L.ShfError("pool after %s reads a channel window; not supported" % l.name)
+                        pooled = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, s["cout"], self.device, out.fmt)
+                        T[s["pool_top"]] = pooled
+                        L.call("shf_maxpool2x2", _ptr(out.t), _ptr(pooled.t), x.n, x.h, x.w, s["cout"], out.fmt, st)
                         self.launches += 1
                 if self.profile:
                     e1 = torch.cuda.Event(enable_timing=True)
                     e1.record()
                     self.events.append((e0, e1))
             elif kind == "pool":
-                out = self._alloc_out(l.tops[0], x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c)
-                L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, st)
+                out = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c, self.device, x.fmt)
+                T[l.tops[0]] = out
+                L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, x.fmt, st)
             elif kind == "deconv":
                 ho = s["s"] * (x.h - 1) + s["k"] - 2 * s["pad"]
                 wo = s["s"] * (x.w - 1) + s["k"] - 2 * s["pad"]
-                out = self._alloc_out(l.tops[0], x.n, ho, wo, x.c)
+                out = self._alloc_out(l.tops[0], x.n, ho, wo, x.c, fmt)
                 L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
-                       s["pad"], out.ctot, out.c_off, st)
+                       s["pad"], out.ctot, out.c_off, x.fmt, out.fmt, st)
             self.launches += 1
 
     def run_tail(self, n_img, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False, det_thresh=0.05):

@@ -17,22 +17,24 @@ _lib = None
 
 c_void_p, c_int, c_float, c_double, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
 
+FMT_H2, FMT_HF8 = 0, 1          # SHF_FMT_* of include/shf_b200.h
+
 # name -> (restype, argtypes); must list every symbol include/shf_b200.h declares
 SIGNATURES = {
     "shf_last_error": (C.c_char_p, []),
     "shf_abi_version": (c_int, []),
     "shf_device_info": (c_int, [c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_ll)]),
     "shf_conv_igemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_int, c_int, c_float, c_int, c_void_p]),
+                               c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "shf_conv_igemm_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                    c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+                                    c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "shf_set_conv_impl": (c_int, [c_int]),
-    "shf_conv1_c3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "shf_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "shf_conv1_c3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "shf_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_deconv_depthwise": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_int, c_void_p]),
-    "shf_h2_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "shf_nchw_to_h2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_void_p]),
+    "shf_h2_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "shf_nchw_to_h2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_preprocess_level": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
                                      C.POINTER(c_double), c_void_p]),
     "shf_head_decode": (c_int, [C.POINTER(c_void_p), c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -57,7 +59,7 @@ SIGNATURES = {
                              c_int]),
     "shf_bbox_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "shf_debug_conv_direct": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 

@@ -25,7 +25,21 @@ from . import lib as L
 from .graph import NetSpec, TEST as _TEST, TRAIN as _TRAIN, load_weights
 
 TRAIN, TEST = _TRAIN, _TEST
-_state = {"device": 0, "mode": "gpu"}
+def _env_fast_min_scale():
+    """SHF_FAST_MIN_SCALE: 'none' = split-fp16 operands for every forward, a number = the im_info scale from which
+    the fast f16+f8 operand format is used (default 0.5, see engine.GpuNet)."""
+    import os
+    v = os.environ.get("SHF_FAST_MIN_SCALE", "0.5").strip().lower()
+    return None if v in ("none", "off", "") else float(v)
+
+
+_state = {"device": 0, "mode": "gpu", "fast_min_scale": _env_fast_min_scale()}
+
+
+def set_fast_min_scale(value):
+    """Not a pycaffe function: operand-format policy of Nets constructed afterwards (None = always precise)."""
+    _state["fast_min_scale"] = None if value is None else float(value)
+
 
 
 def set_mode_gpu():
@@ -115,7 +129,8 @@ class Net(object):
         if int(phase) != TEST:
             raise RuntimeError("only the TEST phase (inference) is implemented")
         from .engine import GpuNet
-        self._engine = GpuNet(self._spec, self._params, "cuda:%d" % _state["device"], **_hot_path_cfg())
+        self._engine = GpuNet(self._spec, self._params, "cuda:%d" % _state["device"],
+                              fast_min_scale=_state["fast_min_scale"], **_hot_path_cfg())
         shapes = self._spec.infer_shapes({})
         self.blobs = OrderedDict((n, Blob(self, n, shapes[n])) for n in self._spec.blob_names)
         self.inputs = list(self._spec.inputs)

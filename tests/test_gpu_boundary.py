@@ -80,10 +80,12 @@ def test_net_surface_and_forward_like_lib_test(deployed):
             d = np.ascontiguousarray(blob[..., ::-1]) if flip else blob
             probs, boxes = forward_net_like_reference(net, {"data": d}, s, flip)
             rp, rb = OD.forward_level(onet, d, s, flip)
-            assert probs.shape == rp.shape and boxes[:, :4].shape == rb.shape
+            # a score within float noise of SCORE_THRESH may fall on either side of it
+            assert abs(len(probs) - len(rp)) <= max(2, len(rp) // 500) and boxes.shape[0] == probs.shape[0]
+            n = min(len(probs), len(rp))
             # same row order unless two scores are within float noise of each other: compare sorted-by-score sets
-            assert np.abs(np.sort(probs[:, 1]) - np.sort(rp[:, 1])).max() < 1e-3
-            k = min(50, len(rp))
+            assert np.abs(np.sort(probs[:, 1])[::-1][:n] - np.sort(rp[:, 1])[::-1][:n]).max() < 1e-3
+            k = min(50, n)
             assert np.abs(boxes[:k, :4] - rb[:k]).max() < 1e-2 or np.abs(np.sort(boxes[:k, 0]) - np.sort(rb[:k, 0])).max() < 1e-2
     # views alias blob storage: an in-place edit is visible through net.blobs (what the flip fix relies on)
     out = net.forward(data=net.blobs["data"].data.copy(), im_info=net.blobs["im_info"].data.copy())
@@ -92,7 +94,17 @@ def test_net_surface_and_forward_like_lib_test(deployed):
     # an intermediate blob is readable after the forward (lazy device->host sync) and matches the oracle
     got = net.blobs["conv5_3"].data
     want = onet.blobs["conv5_3"]
-    assert got.shape == want.shape and np.abs(got - want).max() / np.abs(want).max() < 2e-5
+    # this level has im_scale > 0.5, i.e. it ran on the fast f16+f8 operand format (2^-15-class operands)
+    assert got.shape == want.shape and np.abs(got - want).max() / np.abs(want).max() < 5e-4
+    caffe.set_fast_min_scale(None)
+    try:
+        pnet = caffe.Net(str(proto), str(model), caffe.TEST)
+        pnet.blobs["data"].reshape(*net.blobs["data"].data.shape)
+        pnet.forward(data=net.blobs["data"].data.copy(), im_info=net.blobs["im_info"].data.copy())
+        got = pnet.blobs["conv5_3"].data
+        assert np.abs(got - want).max() / np.abs(want).max() < 2e-5          # split-fp16 operands on request
+    finally:
+        caffe.set_fast_min_scale(0.5)
     with pytest.raises(Exception, match="fused"):
         net.blobs["cls_prob_output"].data
 

@@ -49,7 +49,7 @@ def relerr(a, b):
 
 def test_library_loads_and_reports_b200():
     lib = L.load()
-    assert lib.shf_abi_version() == 1
+    assert lib.shf_abi_version() == 2
     sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
     L.call("shf_device_info", 0, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem))
     assert maj.value == 10, "built for sm_100a only"
@@ -70,7 +70,7 @@ def test_conv1_c3_matches_oracle():
     w = (rng.randn(64, 3, 3, 3) * 0.27).astype(F32)
     b = (rng.randn(64) * 0.05).astype(F32)
     out = H2.empty(1, 37, 53, 64, DEV)
-    L.call("shf_conv1_c3", _ptr(dev(x)), _ptr(dev(w)), _ptr(dev(b)), _ptr(out.t), 1, 37, 53, 64, 1, _stream())
+    L.call("shf_conv1_c3", _ptr(dev(x)), _ptr(dev(w)), _ptr(dev(b)), _ptr(out.t), 1, 37, 53, 64, 1, 0, _stream())
     got = out.to_nchw().cpu().numpy()
     ref = OL.relu(OL.conv(x, w, b, pad=(1, 1)))
     assert relerr(got, ref) < 2e-6
@@ -102,7 +102,7 @@ def test_conv_igemm_matches_oracle(cin, cout, H, W, k, dil, ctot, coff, relu):
     xin = H2.from_nchw(dev(x))
     out = H2(torch.zeros((2, 1, H, W, ctot), dtype=torch.float16, device=DEV), coff, cout)
     L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), 1, H, W, cin, cout, k, dil,
-           ctot, coff, float(2.0 ** -kexp), relu, _stream())
+           ctot, coff, float(2.0 ** -kexp), relu, 0, 0, _stream())
     torch.cuda.synchronize()
     got = out.to_nchw().cpu().numpy()
     pad = dil if k == 3 else 0
@@ -117,7 +117,7 @@ def test_conv_igemm_matches_oracle(cin, cout, H, W, k, dil, ctot, coff, relu):
     # the validation kernel agrees too (it is what big-size tests lean on)
     out2 = H2.empty(1, H, W, cout, DEV)
     L.call("shf_debug_conv_direct", _ptr(xin.t), _ptr(dev(w_eff)), _ptr(dev(b)), _ptr(out2.t), 1, H, W, cin, cout, k,
-           dil, pad, cout, 0, relu, _stream())
+           dil, pad, cout, 0, relu, 0, 0, _stream())
     assert relerr(out2.to_nchw().cpu().numpy(), ref) < 3e-6
 
 
@@ -134,7 +134,7 @@ def test_conv_relu_pool_fused(cin, cout, H, W, write_full):
     full = H2.empty(2, H, W, cout, DEV) if write_full else None
     pooled = H2(torch.zeros((2, 2, H // 2, W // 2, cout + 64), dtype=torch.float16, device=DEV), 64, cout)
     L.call("shf_conv_igemm_pool", _ptr(xin.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(full.t if full else None),
-           _ptr(pooled.t), 2, H, W, cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, _stream())
+           _ptr(pooled.t), 2, H, W, cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, 0, 0, _stream())
     ref = OL.relu(OL.conv(x, w_eff, b, pad=(1, 1)))
     refp = OL.max_pool(ref)
     got = pooled.to_nchw().cpu().numpy()
@@ -153,7 +153,7 @@ def test_conv_igemm_batch2():
     xin = H2.from_nchw(dev(x))
     out = H2.empty(2, 18, 20, 64, DEV)
     L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed)), C.c_void_p(0), _ptr(out.t), 2, 18, 20, 64, 64, 3, 1, 64, 0,
-           float(2.0 ** -kexp), 0, _stream())
+           float(2.0 ** -kexp), 0, 0, 0, _stream())
     assert relerr(out.to_nchw().cpu().numpy(), OL.conv(x, w_eff, None, pad=(1, 1))) < 3e-6
 
 
@@ -162,7 +162,7 @@ def test_maxpool(H, W):
     x = h2_roundtrip_np((np.random.RandomState(2).randn(1, 64, H, W) * 30).astype(F32))
     xin = H2.from_nchw(dev(x))
     out = H2.empty(1, (H + 1) // 2, (W + 1) // 2, 64, DEV)
-    L.call("shf_maxpool2x2", _ptr(xin.t), _ptr(out.t), 1, H, W, 64, _stream())
+    L.call("shf_maxpool2x2", _ptr(xin.t), _ptr(out.t), 1, H, W, 64, 0, _stream())
     assert np.array_equal(out.to_nchw().cpu().numpy(), OL.max_pool(x))
 
 
@@ -173,11 +173,161 @@ def test_deconv_depthwise_into_concat_window():
     w = OL.bilinear_filler((c, 1, 4, 4)) * (1 + 0.1 * rng.rand(c, 1, 1, 1)).astype(F32)
     xin = H2.from_nchw(dev(x))
     dst = torch.zeros((2, 1, 2 * H, 2 * W, 512), dtype=torch.float16, device=DEV)
-    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(w)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 0, _stream())
+    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(w)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 0, 0, 0, _stream())
     got = H2(dst, 0, c).to_nchw().cpu().numpy()
     ref = OL.deconv(x, w, None, pad=(1, 1), stride=(2, 2), group=c)
     assert relerr(got, ref) < 1e-6
     assert torch.all(dst[..., c:] == 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fast operand format "hf8" (fp16 hi plane + 8-bit-float correction plane, include/shf_b200.h)
+# ---------------------------------------------------------------------------------------------------------------
+def _e5m2(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=F32)).to(torch.float8_e5m2).to(torch.float32).numpy()
+
+
+def _e4m3_bytes_to_f32(b):
+    return torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).to(torch.float32).numpy()
+
+
+def hf8_planes_np(x):
+    """(hi as f32, al8 * 2^-10... as the three operand planes the tensor core sees: ah, al8 (scaled by 2^10), ah8)"""
+    x = np.asarray(x, F32)
+    ah = x.astype(np.float16).astype(F32)
+    al8 = _e5m2((x - ah) * F32(1024.0))
+    ah8 = _e5m2(ah)
+    return ah, al8, ah8
+
+
+def hf8_roundtrip_np(x):
+    ah, al8, _ = hf8_planes_np(x)
+    return (ah.astype(np.float64) + al8.astype(np.float64) / 1024.0).astype(F32)
+
+
+def hf8_conv_model(x, packed8, kexp, cout, cin, k, pad, dil, bias, relu):
+    """What the fast conv computes, in float64: ah*wh + (al8*wh8 + ah8*wl8), all at scale 2^kexp."""
+    ah, al8, ah8 = hf8_planes_np(x)
+    wh = packed8[0].astype(np.float64).reshape(k, k, cout, cin).transpose(2, 3, 0, 1)
+    p1 = _e4m3_bytes_to_f32(packed8[1].view(np.uint8)).reshape(k * k, cout, cin // 64, 2, 64)
+    wh8 = p1[:, :, :, 0].reshape(k, k, cout, cin).transpose(2, 3, 0, 1).astype(np.float64)
+    wl8 = p1[:, :, :, 1].reshape(k, k, cout, cin).transpose(2, 3, 0, 1).astype(np.float64)
+    cv = lambda a, w: torch.nn.functional.conv2d(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)),
+                                                 torch.from_numpy(np.ascontiguousarray(w)), None, padding=pad,
+                                                 dilation=dil).numpy()
+    y = (cv(ah, wh) + cv(al8, wh8) + cv(ah8, wl8)) * 2.0 ** -kexp
+    if bias is not None:
+        y = y + bias.astype(np.float64)[None, :, None, None]
+    if relu:
+        y = np.maximum(y, 0)
+    return y
+
+
+def test_hf8_roundtrip():
+    x = (np.random.RandomState(0).randn(2, 128, 9, 13) * 50).astype(F32)
+    x[0, :, 0, 0] = np.float32(2.0) ** np.arange(-64, 64)[:128].clip(-24, 15)       # wide exponent range
+    t = H2.from_nchw(dev(x), fmt=1)
+    back = t.to_nchw().cpu().numpy()
+    assert np.array_equal(back, hf8_roundtrip_np(x))
+    assert relerr(back, x) < 2 ** -14
+    # plane 1 really holds [64 x e5m2(lo * 2^10) | 64 x e5m2(hi)] per pixel and 64-channel block
+    p1 = t.t[1].view(torch.uint8).reshape(2, 9, 13, 2, 2, 64).cpu()
+    ah, al8, ah8 = hf8_planes_np(x)
+    got_al8 = p1[:, :, :, :, 0].view(torch.float8_e5m2).to(torch.float32).numpy().reshape(2, 9, 13, 128).transpose(0, 3, 1, 2)
+    got_ah8 = p1[:, :, :, :, 1].view(torch.float8_e5m2).to(torch.float32).numpy().reshape(2, 9, 13, 128).transpose(0, 3, 1, 2)
+    assert np.array_equal(got_al8, al8) and np.array_equal(got_ah8, ah8)
+
+
+HF8_CONV_CASES = [
+    # cin, cout, H, W, k, dil, ctot, coff, relu, out_fmt
+    (64, 64, 24, 40, 3, 1, 64, 0, 1, 1),
+    (64, 128, 21, 35, 3, 1, 128, 0, 1, 0),
+    (128, 128, 30, 30, 3, 2, 128, 0, 1, 0),      # dilated head: reads hf8, writes h2 for the detection tail
+    (128, 128, 30, 30, 3, 4, 128, 0, 1, 1),
+    (512, 256, 11, 14, 1, 1, 512, 256, 1, 1),    # 1x1 into a concat window
+    (256, 512, 16, 16, 3, 1, 512, 0, 0, 1),
+    (512, 512, 8, 8, 3, 1, 512, 0, 1, 1),
+    (64, 64, 5, 7, 3, 1, 64, 0, 1, 1),
+]
+
+
+@pytest.mark.parametrize("impl", [8, 7])
+@pytest.mark.parametrize("cin,cout,H,W,k,dil,ctot,coff,relu,ofmt", HF8_CONV_CASES)
+def test_conv_igemm_hf8_matches_operand_model(cin, cout, H, W, k, dil, ctot, coff, relu, ofmt, impl):
+    """The fast conv (1 fp16 + 1 fp8 MMA per 16 channels) equals its float64 operand model to accumulation accuracy,
+    and stays within ~1e-4 of the fp32 convolution (2^-15-class operands)."""
+    from smallhardface_b200.engine import pack_conv_weights_hf8
+    rng = np.random.RandomState(cin + cout + H + W + k + dil)
+    x = (np.abs(rng.randn(1, cin, H, W)) * 40 * (rng.rand(1, cin, H, W) > 0.4)).astype(F32)
+    w = (rng.randn(cout, cin, k, k) * np.sqrt(2.0 / (cin * k * k))).astype(F32)
+    b = (rng.randn(cout) * 0.05).astype(F32)
+    packed8, kexp = pack_conv_weights_hf8(w)
+    pad = dil if k == 3 else 0
+    model = hf8_conv_model(x, packed8, kexp, cout, cin, k, pad, dil, b, relu)
+    xin = H2.from_nchw(dev(x), fmt=1)
+    out = H2(torch.zeros((2, 1, H, W, ctot), dtype=torch.float16, device=DEV), coff, cout, fmt=ofmt)
+    L.call("shf_set_conv_impl", impl)
+    try:
+        L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed8)), _ptr(dev(b)), _ptr(out.t), 1, H, W, cin, cout, k, dil,
+               ctot, coff, float(2.0 ** -kexp), relu, 1, ofmt, _stream())
+        torch.cuda.synchronize()
+    finally:
+        L.call("shf_set_conv_impl", 8)
+    got = out.to_nchw().cpu().numpy()
+    want = model.astype(F32) if ofmt == 0 else hf8_roundtrip_np(model.astype(F32))
+    tol = 3e-6 if ofmt == 0 else 2 ** -13         # an hf8 destination re-quantises (a 1-ulp flip of hi moves lo's grid)
+    assert relerr(got, want) < tol, "rel err vs operand model %.3e" % relerr(got, want)
+    ref = OL.conv(x, w, b, pad=(pad, pad), dilation=(dil, dil))
+    if relu:
+        ref = OL.relu(ref)
+    assert relerr(got, ref) < 2e-4, "rel err vs fp32 conv %.3e" % relerr(got, ref)
+    if ctot != cout:
+        full = H2(out.t, fmt=ofmt).to_nchw().cpu().numpy()
+        assert np.all(full[:, :coff] == 0) and np.all(full[:, coff + cout:] == 0)
+
+
+def test_conv_relu_pool_fused_hf8():
+    from smallhardface_b200.engine import pack_conv_weights_hf8
+    cin, cout, H, W = 128, 128, 18, 22
+    rng = np.random.RandomState(7)
+    x = np.abs(rng.randn(2, cin, H, W) * 20).astype(F32)
+    w = (rng.randn(cout, cin, 3, 3) * np.sqrt(2.0 / (cin * 9))).astype(F32)
+    b = (rng.randn(cout) * 0.5).astype(F32)
+    packed8, kexp = pack_conv_weights_hf8(w)
+    model = hf8_conv_model(x, packed8, kexp, cout, cin, 3, 1, 1, b, 1).astype(F32)
+    xin = H2.from_nchw(dev(x), fmt=1)
+    full = H2.empty(2, H, W, cout, DEV, fmt=1)
+    pooled = H2(torch.zeros((2, 2, H // 2, W // 2, cout + 64), dtype=torch.float16, device=DEV), 64, cout, fmt=1)
+    L.call("shf_conv_igemm_pool", _ptr(xin.t), _ptr(dev(packed8)), _ptr(dev(b)), _ptr(full.t), _ptr(pooled.t), 2, H, W,
+           cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, 1, 1, _stream())
+    assert relerr(full.to_nchw().cpu().numpy(), model) < 2 ** -13
+    assert relerr(pooled.to_nchw().cpu().numpy(), OL.max_pool(model)) < 2 ** -13
+    assert torch.all(pooled.t[0][..., :64] == 0)
+
+
+def test_simt_layers_hf8():
+    """conv1_1 / max pool / depthwise deconv reading and writing the fast format."""
+    rng = np.random.RandomState(11)
+    x = (rng.rand(1, 3, 20, 28) * 255 - 110).astype(F32)
+    w = (rng.randn(64, 3, 3, 3) * 0.27).astype(F32)
+    b = (rng.randn(64) * 0.05).astype(F32)
+    out = H2.empty(1, 20, 28, 64, DEV, fmt=1)
+    L.call("shf_conv1_c3", _ptr(dev(x)), _ptr(dev(w)), _ptr(dev(b)), _ptr(out.t), 1, 20, 28, 64, 1, 1, _stream())
+    c1 = out.to_nchw().cpu().numpy()
+    ref = OL.relu(OL.conv(x, w, b, pad=(1, 1)))
+    assert relerr(c1, ref) < 2 ** -14
+    pooled = H2.empty(1, 10, 14, 64, DEV, fmt=1)
+    L.call("shf_maxpool2x2", _ptr(out.t), _ptr(pooled.t), 1, 20, 28, 64, 1, _stream())
+    assert np.array_equal(pooled.to_nchw().cpu().numpy(), OL.max_pool(c1))      # max of representable values, re-split exactly
+    c, H, W = 256, 9, 11
+    xd = hf8_roundtrip_np(np.abs(rng.randn(1, c, H, W) * 20).astype(F32))
+    wd = OL.bilinear_filler((c, 1, 4, 4)) * (1 + 0.1 * rng.rand(c, 1, 1, 1)).astype(F32)
+    xin = H2.from_nchw(dev(xd), fmt=1)
+    dst = torch.zeros((2, 1, 2 * H, 2 * W, 512), dtype=torch.float16, device=DEV)
+    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(wd)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 256, 1, 1, _stream())
+    got = H2(dst, 256, c, fmt=1).to_nchw().cpu().numpy()
+    assert relerr(got, OL.deconv(xd, wd, None, pad=(1, 1), stride=(2, 2), group=c)) < 2 ** -14
+    assert torch.all(dst[0][..., :256] == 0)
 
 
 @pytest.mark.parametrize("hw,scale,flip", [((224, 224), 1.0, 0), ((224, 224), 1.3671875, 1), ((96, 130), 0.29296875, 0),

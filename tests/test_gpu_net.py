@@ -52,7 +52,9 @@ def nets(request, tmp_path_factory):
     proto, model = deploy.write_synthetic_deployment(str(d), dilation=request.param)
     spec = NetSpec(cp.read_net_text(proto))
     params = load_weights(spec, cp.read_net_binary(model))
-    return request.param, proto, model, GpuNet(spec, params, "cuda:0", fuse_pool=False), OracleNet(proto, model, engine="sgemm", fast=True)
+    # fast_min_scale=None: split-fp16 operands everywhere, so the per-blob bounds below are the precise format's
+    return (request.param, proto, model, GpuNet(spec, params, "cuda:0", fuse_pool=False, fast_min_scale=None),
+            OracleNet(proto, model, engine="sgemm", fast=True))
 
 
 def test_net_forward_224_blobs_and_outputs(nets):
@@ -87,10 +89,60 @@ def test_net_forward_224_blobs_and_outputs(nets):
     assert ws < SCORE_TOL and wb < BOX_TOL
 
 
+def test_net_forward_224_fast_operand_format(nets):
+    """BASELINE config 1 through the fast (fp16 + fp8-correction) operand format: intermediate blobs carry
+    ~2^-15-class error, the outputs still meet the reference tolerances (scale 1.0: no magnification)."""
+    dil, proto, model, gnet, onet = nets
+    fast = GpuNet(gnet.spec, load_weights(gnet.spec, cp.read_net_binary(model)), "cuda:0", fuse_pool=False, fast_min_scale=0.5)
+    im = parity_image()
+    data = np.ascontiguousarray((im.astype(F32) - np.array([[[102.9801, 115.9465, 122.7717]]])).astype(F32).transpose(2, 0, 1)[None])
+    info = np.array([[224, 224, 1.0]], F32)
+    assert fast.use_fast(info[0][2]) and not fast.use_fast(0.4) and not gnet.use_fast(1.0)
+    ref = onet.forward(data=data, im_info=info)
+    boxes, probs, rows = fast.forward(torch.from_numpy(data).to(DEV), info[0])
+    R = int(rows.item())
+    report = {}
+    for nm in ["conv1_2", "conv3_3", "conv4_3", "conv5_3", "conv4_fuse", "conv4_fuse_final"]:
+        got, want = fast.blob_nchw(nm).cpu().numpy(), onet.blobs[nm]
+        report[nm] = float(np.abs(got - want).max() / np.abs(want).max())
+    print("fast format per-blob max rel err:", {k: "%.2e" % v for k, v in report.items()})
+    assert 1e-7 < max(report.values()) < 5e-4, report          # really the reduced format, and only that much worse
+    assert np.abs(fast.blob_nchw("cls_prob_reshape_output").cpu().numpy() - onet.blobs["cls_prob_reshape_output"]).max() < SCORE_TOL
+    gb, gp = boxes[:R].cpu().numpy(), probs[:R].cpu().numpy()
+    ws, wb = match_rows(gb[:, 1:], gp[:, 1], ref["boxes"][:, 1:], ref["cls_prob"][:, 1])
+    print("fast format rows %d (ref %d): worst score err %.2e, worst box err %.2e px" % (R, len(ref["boxes"]), ws, wb))
+    assert ws < SCORE_TOL and wb < BOX_TOL
+
+
+def test_fast_format_parity_at_its_smallest_level():
+    """The adaptive policy's worst case: the 600-px pyramid level of a 1024x1024 image (im_scale 0.586, box errors
+    magnified x1.7 on the way back to raw-image px) is the smallest level that runs on the fast operand format."""
+    import tempfile, os
+    from oracle import preprocess as PRE
+    proto, model = deploy.write_synthetic_deployment(os.path.join(tempfile.gettempdir(), "shf_b200_deploy"), dilation=True)
+    onet = OracleNet(proto, model, engine="torch", fast=True)
+    im = deploy.synthetic_image(3)
+    cfg = DetectConfig(scales=(600, 601), flip=False, thresh=0.002)      # two scales -> pyramid mode; pass 0 is level 600
+    det = Detector(proto, model, "cuda:0", cfg)
+    s = PRE.pyramid_scales(im.shape, (600, 601))[0]
+    assert 0.5 <= s < 0.6 and det.net.use_fast(s)
+    b = det.detect_device(det.upload([im]))
+    n0 = int(b["offs"][0, 1].item())
+    raw = b["dets"][0, :n0].cpu().numpy()
+    blob = PRE.get_image_blobs(im, [s])[0]
+    p, bx = OD.forward_level(onet, blob, s)
+    ref = np.hstack([bx, p[:, 1:2]])
+    ref = ref[ref[:, 4] > np.float32(0.002)]
+    ws, wb = match_rows(raw[:, :4], raw[:, 4], ref[:, :4], ref[:, 4])
+    print("fast format, level 600 (scale %.4f): rows %d (ref %d) worst score err %.2e worst box err %.2e raw px" %
+          (s, len(raw), len(ref), ws, wb))
+    assert ws < SCORE_TOL and wb < BOX_TOL
+
+
 def test_fused_pool_plan_matches_unfused(nets):
     """The default plan (conv+ReLU+pool in one launch, un-pooled blobs not materialised) gives the same outputs."""
     dil, proto, model, gnet, onet = nets
-    fused = GpuNet(gnet.spec, load_weights(gnet.spec, cp.read_net_binary(model)), "cuda:0")
+    fused = GpuNet(gnet.spec, load_weights(gnet.spec, cp.read_net_binary(model)), "cuda:0", fast_min_scale=None)
     assert fused.fuse_pool and sum(1 for k, l, s in fused.ops if k == "conv" and "pool_top" in s) == 4
     im = parity_image()
     data = np.ascontiguousarray((im.astype(F32) - np.array([[[102.9801, 115.9465, 122.7717]]])).astype(F32).transpose(2, 0, 1)[None])

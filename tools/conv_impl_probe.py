@@ -28,7 +28,7 @@ for impl in impls:
         out = H2.empty(1, H, W, cout, dev)
         try:
             L.call("shf_conv_igemm", _ptr(xin.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0,
-                   float(2.0 ** -kexp), 1, _stream())
+                   float(2.0 ** -kexp), 1, 0, 0, _stream())
             torch.cuda.synchronize()
             got = out.to_nchw().cpu().numpy()
             pad = dil if k == 3 else 0
@@ -48,7 +48,7 @@ for impl in impls:
             w = (np.random.RandomState(0).randn(cout, cin, k, k) * 0.02).astype(np.float32)
             packed, kexp = pack_conv_weights(w)
             wd = torch.from_numpy(packed).to(dev); bd = torch.zeros(cout, device=dev); out = H2.empty(1, H, W, cout, dev)
-            run = lambda: L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0, float(2.0 ** -kexp), 1, _stream())
+            run = lambda: L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0, float(2.0 ** -kexp), 1, 0, 0, _stream())
             run(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
