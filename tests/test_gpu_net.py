@@ -26,13 +26,18 @@ def parity_image(hw=(224, 224), seed=3):
     return np.random.RandomState(seed).randint(0, 256, hw + (3,)).astype(np.uint8)
 
 
-def match_rows(got_boxes, got_scores, ref_boxes, ref_scores, scale=1.0):
+def match_rows(got_boxes, got_scores, ref_boxes, ref_scores, scale=1.0, cap=10000):
     """Every reference row must have a device row within the tolerances (rank swaps between near-equal
     scores are allowed; the row sets must otherwise coincide)."""
     assert abs(len(got_scores) - len(ref_scores)) <= max(2, len(ref_scores) // 500), (len(got_scores), len(ref_scores))
     worst_s = worst_b = 0.0
     used = np.zeros(len(got_scores), bool)
+    # a pass that hit the N_DETS_PER_MODULE cap (proposal_layer.py:186) was cut at a score; rows within float noise of
+    # that score may sit on either side of the cut
+    cut = max(got_scores.min(), ref_scores.min()) if min(len(got_scores), len(ref_scores)) >= cap else -1.0
     for i in range(len(ref_scores)):
+        if ref_scores[i] < cut + SCORE_TOL:
+            continue
         cand = np.where((np.abs(got_scores - ref_scores[i]) < SCORE_TOL) & ~used)[0]
         if cand.size == 0:
             if ref_scores[i] < 0.002 + SCORE_TOL or abs(ref_scores[i] - 0.05) < SCORE_TOL:
@@ -98,6 +103,7 @@ def test_net_forward_224_fast_operand_format(nets):
     data = np.ascontiguousarray((im.astype(F32) - np.array([[[102.9801, 115.9465, 122.7717]]])).astype(F32).transpose(2, 0, 1)[None])
     info = np.array([[224, 224, 1.0]], F32)
     assert fast.use_fast(info[0][2]) and not fast.use_fast(0.4) and not gnet.use_fast(1.0)
+    assert GpuNet.__init__.__defaults__[-1] == 1.3           # the shipped policy: only levels that shrink errors by >= 1.3
     ref = onet.forward(data=data, im_info=info)
     boxes, probs, rows = fast.forward(torch.from_numpy(data).to(DEV), info[0])
     R = int(rows.item())
@@ -114,18 +120,21 @@ def test_net_forward_224_fast_operand_format(nets):
     assert ws < SCORE_TOL and wb < BOX_TOL
 
 
-def test_fast_format_parity_at_its_smallest_level():
-    """The adaptive policy's worst case: the 600-px pyramid level of a 1024x1024 image (im_scale 0.586, box errors
-    magnified x1.7 on the way back to raw-image px) is the smallest level that runs on the fast operand format."""
+@pytest.mark.parametrize("level,policy", [(1400, "default"), (600, 0.5)])
+def test_fast_format_level_parity_1024(level, policy):
+    """Whole pyramid levels of a 1024x1024 bench image on the fast operand format against the oracle, in raw-image px:
+    the 1400-px level (im_scale 1.37) is what the default policy runs fast; the 600-px level (im_scale 0.586, errors
+    magnified x1.7) only with an explicitly lowered fast_min_scale -- it still meets the tolerance, with less margin."""
     import tempfile, os
     from oracle import preprocess as PRE
     proto, model = deploy.write_synthetic_deployment(os.path.join(tempfile.gettempdir(), "shf_b200_deploy"), dilation=True)
     onet = OracleNet(proto, model, engine="torch", fast=True)
     im = deploy.synthetic_image(3)
-    cfg = DetectConfig(scales=(600, 601), flip=False, thresh=0.002)      # two scales -> pyramid mode; pass 0 is level 600
+    kw = {} if policy == "default" else {"fast_min_scale": policy}
+    cfg = DetectConfig(scales=(level, level + 1), flip=False, thresh=0.002, **kw)      # two scales -> pyramid mode; pass 0 is the level
     det = Detector(proto, model, "cuda:0", cfg)
-    s = PRE.pyramid_scales(im.shape, (600, 601))[0]
-    assert 0.5 <= s < 0.6 and det.net.use_fast(s)
+    s = PRE.pyramid_scales(im.shape, (level, level + 1))[0]
+    assert det.net.use_fast(s) and not det.net.use_fast(0.45)
     b = det.detect_device(det.upload([im]))
     n0 = int(b["offs"][0, 1].item())
     raw = b["dets"][0, :n0].cpu().numpy()
@@ -134,8 +143,8 @@ def test_fast_format_parity_at_its_smallest_level():
     ref = np.hstack([bx, p[:, 1:2]])
     ref = ref[ref[:, 4] > np.float32(0.002)]
     ws, wb = match_rows(raw[:, :4], raw[:, 4], ref[:, :4], ref[:, 4])
-    print("fast format, level 600 (scale %.4f): rows %d (ref %d) worst score err %.2e worst box err %.2e raw px" %
-          (s, len(raw), len(ref), ws, wb))
+    print("fast format, level %d (scale %.4f): rows %d (ref %d) worst score err %.2e worst box err %.2e raw px" %
+          (level, s, len(raw), len(ref), ws, wb))
     assert ws < SCORE_TOL and wb < BOX_TOL
 
 
