@@ -134,13 +134,15 @@ SHF_DEVICE void act_store8(__half* px0, size_t plane_elems, int c, const float (
     uint32_t ap[2] = {0u, 0u}, bp[2] = {0u, 0u};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      __half h0, h1;
-      uint8_t a0, b0, a1, b1;
-      split_hf8(v[2 * e], h0, a0, b0);
-      split_hf8(v[2 * e + 1], h1, a1, b1);
-      hp[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      ap[e >> 1] |= ((uint32_t)a0 | ((uint32_t)a1 << 8)) << (16 * (e & 1));
-      bp[e >> 1] |= ((uint32_t)b0 | ((uint32_t)b1 << 8)) << (16 * (e & 1));
+      // pairs: one F2FP packs two fp16 / two e5m2 values
+      const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      const float2 hf = __half22float2(h);
+      const float2 lo = make_float2((v[2 * e] - hf.x) * 1024.f, (v[2 * e + 1] - hf.y) * 1024.f);
+      const uint32_t a2 = (uint32_t)__nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E5M2);
+      const uint32_t b2 = (uint32_t)__nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E5M2);
+      hp[e] = *reinterpret_cast<const uint32_t*>(&h);
+      ap[e >> 1] |= a2 << (16 * (e & 1));
+      bp[e >> 1] |= b2 << (16 * (e & 1));
     }
     *reinterpret_cast<uint4*>(px0 + c) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
     uint8_t* p1 = reinterpret_cast<uint8_t*>(px0 + plane_elems) + hf8_off(c);

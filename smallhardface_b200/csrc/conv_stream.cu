@@ -34,7 +34,8 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kTH = 16, kTW = 8;
 constexpr int kChunkK = 64;
-constexpr int kMaxA = 4, kMaxB = 8;
+constexpr int kMaxA = 4, kMaxB = 9;
+constexpr int kThreads = 384;        // warps 0-3: TMA B / MMA / TMEM alloc / TMA A; warps 4-11: drain + epilogue
 
 struct StreamParams {
   int H, W, batch;
@@ -46,6 +47,8 @@ struct StreamParams {
   int chunks_per_phase;       // G
   int ctot, cout_offset, relu;
   int in_fmt, out_fmt;        // SHF_FMT_* of the input (and weight) planes / of the tensors written
+  int b_resident;             // the whole weight tensor fits the B ring (one stage per (chunk, tap)): load it once per CTA
+  int probe;                  // SHF_PROBE_EPI timing probes (wrong results): 1 = no global stores, 2 = drain only
   float out_scale;
   const float* bias;
   __half* out;                // h2 destination tensor base (plane 0); plane 1 at + plane_elems (nullptr: skip)
@@ -60,7 +63,7 @@ struct StreamParams {
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 template <int BN, int CTAS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,7 +96,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kMaxA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < kMaxB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4 * CTAS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8 * CTAS); }
     fence_mbar_init();
   } else if (warp == 2) {
     if (CTAS == 2) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
@@ -118,14 +121,19 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer: weight stages [B_hi ; B_lo], one per (chunk, tap) =====================
     if (lane == 0) {
-      int itb = 0;
+      // ring position kept as (stage, phase bit): a runtime `it % nb`, `it / nb` costs an integer division per use,
+      // which in the MMA-issuing warp was ~30 % of its cycles (profiles/r01 source view)
+      int sb = 0;
+      uint32_t phb = 0;
+      bool first = true;
       for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
         int nt, x0, y0, img;
         decode_tile(t, nt, x0, y0, img);
+        if (p.b_resident && !first) break;     // weights stay in shared memory for every tile of this CTA
+        first = false;
         for (int cc = 0; cc < p.cin_chunks; ++cc)
-          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
-            const int sb = itb % p.nb;
-            mbar_wait(empty_b(sb), ((itb / p.nb) & 1) ^ 1);
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(empty_b(sb), phb ^ 1);
             if (CTAS == 2) {
               // both CTAs credit the LEADER's barrier; each loads its half of the output channels (hi and lo plane)
               if (rank == 0) mbar_arrive_expect_tx(full_b(sb), 2 * p.b_bytes);
@@ -135,21 +143,25 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               mbar_arrive_expect_tx(full_b(sb), p.b_bytes);
               tma_load_4d(b_stage(sb), &tmap_b, full_b(sb), cc * kChunkK, nt * BN, tap, 0);
             }
+            if (++sb == p.nb) { sb = 0; phb ^= 1; }
           }
       }
-      if (CTAS == 2)      // tail: the leader's multicast commits must have landed here before this CTA may exit
-        for (int k = 0; k < p.nb; ++k, ++itb) mbar_wait(empty_b(itb % p.nb), ((itb / p.nb) & 1) ^ 1);
+      if (CTAS == 2 && !p.b_resident)      // tail: the leader's multicast commits must have landed here before this CTA may exit
+        for (int k = 0; k < p.nb; ++k) {
+          mbar_wait(empty_b(sb), phb ^ 1);
+          if (++sb == p.nb) { sb = 0; phb ^= 1; }
+        }
     }
   } else if (warp == 3) {
     // ===================== TMA producer: activation halos, one per 64-channel chunk =====================
     if (lane == 0) {
-      int ita = 0;
+      int sa = 0;
+      uint32_t pha = 0;
       for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
         int nt, x0, y0, img;
         decode_tile(t, nt, x0, y0, img);
-        for (int cc = 0; cc < p.cin_chunks; ++cc, ++ita) {
-          const int sa = ita % p.na;
-          mbar_wait(empty_a(sa), ((ita / p.na) & 1) ^ 1);
+        for (int cc = 0; cc < p.cin_chunks; ++cc) {
+          mbar_wait(empty_a(sa), pha ^ 1);
           if (CTAS == 2) {
             if (rank == 0) mbar_arrive_expect_tx(full_a(sa), 2 * p.a_tx);
             tma_load_5d_pair(a_stage(sa), &tmap_a, mapa_shared(full_a(sa), 0), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
@@ -157,10 +169,14 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             mbar_arrive_expect_tx(full_a(sa), p.a_tx);
             tma_load_5d(a_stage(sa), &tmap_a, full_a(sa), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
           }
+          if (++sa == p.na) { sa = 0; pha ^= 1; }
         }
       }
       if (CTAS == 2)
-        for (int k = 0; k < p.na; ++k, ++ita) mbar_wait(empty_a(ita % p.na), ((ita / p.na) & 1) ^ 1);
+        for (int k = 0; k < p.na; ++k) {
+          mbar_wait(empty_a(sa), pha ^ 1);
+          if (++sa == p.na) { sa = 0; pha ^= 1; }
+        }
     }
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (warp converged, one elected lane issues; leader CTA only) =====================
@@ -173,7 +189,10 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     constexpr uint32_t b_plane16 = (uint32_t)((BN / CTAS) * 128) >> 4;           // hi rows -> lo rows of a weight stage
     const uint32_t a_plane16 = ((uint32_t)(p.xh * p.xw) * 128u) >> 4;
     const int ktaps = (p.taps == 9) ? 3 : 1;
-    int ita = 0, itb = 0, gp = 0;
+    const uint32_t tap_dx = (uint32_t)p.dil * 128u;                              // bytes to the next tap column
+    const uint32_t tap_dy = (uint32_t)(p.dil * p.xw) * 128u - (uint32_t)ktaps * tap_dx;   // ... and on to the next tap row
+    int sa = 0, sb = 0, gp = 0;
+    uint32_t pha = 0, phb = 0;
     for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
       for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
         const int set = gp & 1;
@@ -183,16 +202,14 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int c_begin = ph * p.chunks_per_phase;
         const int c_end = min(c_begin + p.chunks_per_phase, p.cin_chunks);
         uint32_t opened = 0;                                      // 0 until the set has been overwritten once
-        for (int cc = c_begin; cc < c_end; ++cc, ++ita) {
-          const int sa = ita % p.na;
-          mbar_wait(full_a(sa), (ita / p.na) & 1);
+        for (int cc = c_begin; cc < c_end; ++cc) {
+          mbar_wait(full_a(sa), pha);
           const uint32_t a_base = a_stage(sa);
-          int r = 0, s = 0;
-          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
-            const int sb = itb % p.nb;
-            mbar_wait(full_b(sb), (itb / p.nb) & 1);
+          uint32_t a_off = 0;
+          int s = 0;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(full_b(sb), p.b_resident ? 0u : phb);       // resident: filled once (phase 0)
             tc_fence_after();
-            const uint32_t a_off = (uint32_t)((r * p.dil) * p.xw + s * p.dil) * 128u;
             uint32_t a_lo32 = (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo;
             uint32_t b_lo32 = ((b_stage(sb) & 0x3FFFFu) >> 4) | lbo;
             if (p.in_fmt == SHF_FMT_HF8) {
@@ -232,19 +249,30 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 a_lo32 += 2; b_lo32 += 2;
               }
             }
-            if (CTAS == 2) umma_commit_pair_elect(empty_b(sb)); else umma_commit_elect(empty_b(sb));
-            if (++s == ktaps) { s = 0; ++r; }
+            if (!p.b_resident) {
+              if (CTAS == 2) umma_commit_pair_elect(empty_b(sb)); else umma_commit_elect(empty_b(sb));
+            }
+            if (++sb == p.nb) { sb = 0; phb ^= 1; }
+            a_off += tap_dx;
+            if (++s == ktaps) { s = 0; a_off += tap_dy; }
           }
           if (CTAS == 2) umma_commit_pair_elect(empty_a(sa)); else umma_commit_elect(empty_a(sa));
+          if (++sa == p.na) { sa = 0; pha ^= 1; }
         }
         if (CTAS == 2) umma_commit_pair_elect(acc_full(set)); else umma_commit_elect(acc_full(set));
       }
     }
   } else if (warp >= 4) {
     // ===================== drain + epilogue warps =====================
+    // Eight warps: warp w may only touch TMEM lanes 32*(w%4)..+31, so warps w and w+4 share a pixel quadrant and split
+    // its channels (kCols each).  Two epilogue warps per scheduler hide each other's shuffle / conversion / store
+    // latencies; with four, the epilogue of the 64-channel layers was slower than their main loop.
+    constexpr int kCols = BN / 2;
     const int w = warp - 4;
-    const int m = w * 32 + lane;                 // accumulator row = pixel (y_local * 8 + x_local)
-    const uint32_t lane_addr = (uint32_t)(w * 32) << 16;
+    const int quad = w & 3, half = w >> 2;
+    const int m = quad * 32 + lane;              // accumulator row = pixel (y_local * 8 + x_local)
+    const int col0 = half * kCols;               // first channel of the n-tile this warp owns
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float scale = p.out_scale;
     const uint32_t drained0 = (CTAS == 2) ? mapa_shared(acc_empty(0), 0) : acc_empty(0);   // in the leader
     const uint32_t drained1 = (CTAS == 2) ? mapa_shared(acc_empty(1), 0) : acc_empty(1);
@@ -255,12 +283,12 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // stage this tile's bias slice in shared memory now, so that its global-load latency hides behind the main loop
       // (read per 8-channel group straight from global memory it serialised ~16 L2 round trips into every epilogue)
       float* bias_t = bias_s + (tile_it & 1) * BN;
-      if (m < BN) bias_t[m] = p.bias ? __ldg(p.bias + nt * BN + m) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+      if (w * 32 + lane < BN) bias_t[w * 32 + lane] = p.bias ? __ldg(p.bias + nt * BN + w * 32 + lane) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the eight epilogue warps only
       ++tile_it;
-      float acc[BN];
+      float acc[kCols];
 #pragma unroll
-      for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+      for (int c = 0; c < kCols; ++c) acc[c] = 0.f;
       for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
         const int set = gp & 1;
         mbar_wait(acc_full(set), (gp >> 1) & 1);
@@ -268,19 +296,19 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t base = lane_addr + (uint32_t)set * kSetCols;
         if (p.in_fmt == SHF_FMT_HF8) {
 #pragma unroll
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = 0; c0 < kCols; c0 += 32) {
             uint32_t mq[32];
-            tmem_ld_32x32(base + c0, mq);            // hi*hi + correction partial
+            tmem_ld_32x32(base + col0 + c0, mq);     // hi*hi + correction partial
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e) acc[c0 + e] = __fadd_rn(acc[c0 + e], __uint_as_float(mq[e]));
           }
         } else {
 #pragma unroll
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = 0; c0 < kCols; c0 += 32) {
             uint32_t mq[32], cq[32];
-            tmem_ld_32x32(base + c0, mq);            // hi*hi partial
-            tmem_ld_32x32(base + BN + c0, cq);       // cross partial
+            tmem_ld_32x32(base + col0 + c0, mq);            // hi*hi partial
+            tmem_ld_32x32(base + BN + col0 + c0, cq);       // cross partial
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -289,7 +317,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {                                          // 4 (x2) warps -> the set is free again
+        if (lane == 0) {                                          // 8 (x2) warps -> the set is free again
           if (CTAS == 2) mbar_arrive_cluster(set ? drained1 : drained0);
           else mbar_arrive_cnt(acc_empty(set));
         }
@@ -304,15 +332,16 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       __half* ppx0 = p.pool_out ? p.pool_out + (((size_t)img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
                                                    (size_t)p.pool_ctot
                                 : nullptr;
+      if (p.probe == 2) continue;
 #pragma unroll
-      for (int c = 0; c < BN; c += 8) {
+      for (int c = 0; c < kCols; c += 8) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          v[e] = fmaf(acc[c + e], scale, bias_t[c + e]);
+          v[e] = fmaf(acc[c + e], scale, bias_t[col0 + c + e]);
           if (p.relu) v[e] = fmaxf(v[e], 0.f);
         }
-        if (px0 && inside) act_store8(px0, (size_t)p.plane_elems, p.cout_offset + n0 + c, v, p.out_fmt);
+        if (px0 && inside && (p.probe != 1 || v[0] == 12345.678f)) act_store8(px0, (size_t)p.plane_elems, p.cout_offset + n0 + col0 + c, v, p.out_fmt);
         if (p.pool_out) {                                   // warp-uniform branch: all lanes take part in the shuffles
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -321,7 +350,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
             v[e] = q;
           }
-          if (pool_writer) act_store8(ppx0, (size_t)p.pool_plane_elems, p.pool_coffset + n0 + c, v, p.out_fmt);
+          if (pool_writer && (p.probe != 1 || v[0] == 12345.678f)) act_store8(ppx0, (size_t)p.pool_plane_elems, p.pool_coffset + n0 + col0 + c, v, p.out_fmt);
         }
       }
     }
@@ -343,11 +372,11 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamPara
     attr = true;
   }
   if (CTAS == 1) {
-    conv_stream_kernel<BN, CTAS><<<grid, 256, smem_bytes, stream>>>(ta, tb, p);
+    conv_stream_kernel<BN, CTAS><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -413,10 +442,17 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.a_bytes = (p.a_tx + 1023) & ~1023;
   p.b_bytes = 2 * (bn / ctas) * 128;          // per CTA: its share of the output channels, hi + lo plane
   const int budget = 227 * 1024 - 1024 - 1536;      // alignment slack; barriers (512) + staged bias (1024)
-  p.na = (p.taps == 1) ? kMaxA : 2;
-  while (p.na > 1 && p.na * p.a_bytes + 3 * p.b_bytes > budget) --p.na;
+  // A-ring depth: a halo stage lasts taps x 4 k-steps of MMAs; when that is short (one 64-channel chunk per tile at
+  // BN = 64: ~2-3k cycles, or 1x1 convs) two stages do not cover the ~4k cycles a 46 KB halo takes to arrive
+  p.na = (p.taps == 1) ? kMaxA : ((bn == 64 || p.cin_chunks == 1) ? 3 : 2);
+  if (const char* e = getenv("SHF_PROBE_NA")) { int v = atoi(e); if (v >= 1 && v <= kMaxA) p.na = v; }
+  while (p.na > 1 && p.na * p.a_bytes + 4 * p.b_bytes > budget) --p.na;
   p.nb = (budget - p.na * p.a_bytes) / p.b_bytes;
   if (p.nb > kMaxB) p.nb = kMaxB;
+  // conv1_2-class layers (one N tile, 9 stages of weights in all): keep the weights in shared memory for the whole
+  // kernel -- streaming them again for every 128-pixel tile was most of that layer's L2->SM traffic
+  p.b_resident = (cout == bn && p.taps * p.cin_chunks <= p.nb && p.na >= 2 && !getenv("SHF_PROBE_NO_RESIDENT")) ? 1 : 0;
+  if (p.b_resident) p.nb = p.taps * p.cin_chunks;
   if (const char* e = getenv("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
   SHF_REQUIRE(p.nb >= 2, "shf_conv_igemm: halo tile of %d bytes leaves no room for the weight ring", p.a_bytes);
   p.tiles_x = ((W + kTW - 1) / kTW + ctas - 1) / ctas;          // tile pairs along x when ctas == 2
@@ -429,6 +465,8 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.cout_offset = out_channel_offset;
   p.relu = relu;
   p.in_fmt = in_format;
+  p.probe = 0;
+  if (const char* e = getenv("SHF_PROBE_EPI")) p.probe = atoi(e);
   p.out_fmt = out_format;
   p.out_scale = out_scale;
   p.bias = bias;
