@@ -296,6 +296,32 @@ SHF_DEVICE void umma_commit_elect(uint32_t bar) {
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
       ::"r"(bar) : "memory");
 }
+// ---- single-thread variants (call inside ONE `if (issuer)` region per group of MMAs; issuer = elect_one() once) ----
+// Electing per instruction wraps every MMA in its own ELECT / branch / reconvergence pair (~50 cycles per MMA measured:
+// slower than a 32-cycle N = 64 MMA, so the tensor pipe of the 64-channel layers idled 40 % of the time).
+#define SHF_DEFINE_UMMA(NAME, GROUP, KIND)                                                                          \
+  SHF_DEVICE void NAME(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, \
+                       uint32_t accumulate) {                                                                       \
+    asm volatile(                                                                                                   \
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                             \
+        "mov.b64 da, {%1, %2};\n\t"                                                                                 \
+        "mov.b64 db, {%3, %4};\n\t"                                                                                 \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                                 \
+        "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),                \
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)                                     \
+        : "memory");                                                                                                \
+  }
+SHF_DEFINE_UMMA(umma1_f16, "1", "f16")
+SHF_DEFINE_UMMA(umma1_f8, "1", "f8f6f4")
+SHF_DEFINE_UMMA(umma2_f16, "2", "f16")
+SHF_DEFINE_UMMA(umma2_f8, "2", "f8f6f4")
+#undef SHF_DEFINE_UMMA
+SHF_DEVICE void umma2_commit(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
+      ::"r"(bar) : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 SHF_DEVICE void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

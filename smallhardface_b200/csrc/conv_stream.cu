@@ -162,7 +162,9 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         decode_tile(t, nt, x0, y0, img);
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
           mbar_wait(empty_a(sa), pha ^ 1);
-          if (CTAS == 2) {
+          if (p.probe & 4) {                     // timing probe: no activation loads at all
+            if (rank == 0) mbar_arrive(full_a(sa));
+          } else if (CTAS == 2) {
             if (rank == 0) mbar_arrive_expect_tx(full_a(sa), 2 * p.a_tx);
             tma_load_5d_pair(a_stage(sa), &tmap_a, mapa_shared(full_a(sa), 0), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
           } else {
@@ -191,6 +193,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int ktaps = (p.taps == 9) ? 3 : 1;
     const uint32_t tap_dx = (uint32_t)p.dil * 128u;                              // bytes to the next tap column
     const uint32_t tap_dy = (uint32_t)(p.dil * p.xw) * 128u - (uint32_t)ktaps * tap_dx;   // ... and on to the next tap row
+    const bool issuer = elect_one();          // the one lane that talks to the tensor core
     int sa = 0, sb = 0, gp = 0;
     uint32_t pha = 0, phb = 0;
     for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
@@ -212,54 +215,63 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tc_fence_after();
             uint32_t a_lo32 = (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo;
             uint32_t b_lo32 = ((b_stage(sb) & 0x3FFFFu) >> 4) | lbo;
-            if (p.in_fmt == SHF_FMT_HF8) {
-              // hi*hi as one f16 MMA, the first-order correction [al8 | ah8] x [wh8 | wl8] as one f8 MMA over the
-              // same 32 bytes of K per operand row (plane 1 of either stage), both into the same accumulator
+            if (issuer) {                       // ONE single-thread region per weight stage: 8 or 12 MMAs + the stage release
+              if (p.probe & 8) {                 // timing probe: no MMAs, only the barrier traffic
+              } else if (p.in_fmt == SHF_FMT_HF8) {
+                // hi*hi as one f16 MMA, the first-order correction [al8 | ah8] x [wh8 | wl8] as one f8 MMA over the
+                // same 32 bytes of K per operand row (plane 1 of either stage), both into the same accumulator
 #pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) {
-                if (CTAS == 2) {
-                  umma_f16_pair_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                  umma_f8_pair_elect_lohi(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
-                } else {
-                  umma_f16_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                  umma_f8_elect_lohi(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+                for (int k = 0; k < kChunkK / 16; ++k) {
+                  if (CTAS == 2) {
+                    umma2_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+                    umma2_f8(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+                  } else {
+                    umma1_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+                    umma1_f8(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+                  }
+                  opened = 1u;
+                  a_lo32 += 2; b_lo32 += 2;
                 }
-                opened = 1u;
-                a_lo32 += 2; b_lo32 += 2;
-              }
-            } else if (CTAS == 2) {
-              // the pair's weight stage is split by output channel, so hi and lo rows are separate N = BN operands:
-              //   main += A_hi x B_hi ;  cross += A_hi x B_lo ;  cross += A_lo x B_hi
+              } else if (CTAS == 2) {
+                // the pair's weight stage is split by output channel, so hi and lo rows are separate N = BN operands:
+                //   main += A_hi x B_hi ;  cross += A_hi x B_lo ;  cross += A_lo x B_hi
 #pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) {
-                umma_f16_pair_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                umma_f16_pair_elect_lohi(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
-                umma_f16_pair_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
-                opened = 1u;
-                a_lo32 += 2; b_lo32 += 2;
-              }
-            } else {
+                for (int k = 0; k < kChunkK / 16; ++k) {
+                  umma2_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+                  umma2_f16(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
+                  umma2_f16(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+                  opened = 1u;
+                  a_lo32 += 2; b_lo32 += 2;
+                }
+              } else {
 #pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) {
-                // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
-                umma_f16_elect_lohi(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
-                // cross += A_lo x B_hi
-                umma_f16_elect_lohi(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
-                opened = 1u;
-                a_lo32 += 2; b_lo32 += 2;
+                for (int k = 0; k < kChunkK / 16; ++k) {
+                  // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
+                  umma1_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
+                  // cross += A_lo x B_hi
+                  umma1_f16(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+                  opened = 1u;
+                  a_lo32 += 2; b_lo32 += 2;
+                }
+              }
+              if (!p.b_resident) {
+                if (CTAS == 2) umma2_commit(empty_b(sb)); else umma_commit(empty_b(sb));
+              }
+              if (tap == p.taps - 1) {          // last tap of this halo: hand the A stage back as well
+                if (CTAS == 2) umma2_commit(empty_a(sa)); else umma_commit(empty_a(sa));
+                if (cc == c_end - 1) {          // ... and, after the phase's last chunk, publish the accumulator set
+                  if (CTAS == 2) umma2_commit(acc_full(set)); else umma_commit(acc_full(set));
+                }
               }
             }
-            if (!p.b_resident) {
-              if (CTAS == 2) umma_commit_pair_elect(empty_b(sb)); else umma_commit_elect(empty_b(sb));
-            }
+            __syncwarp();
+            opened = 1u;
             if (++sb == p.nb) { sb = 0; phb ^= 1; }
             a_off += tap_dx;
             if (++s == ktaps) { s = 0; a_off += tap_dy; }
           }
-          if (CTAS == 2) umma_commit_pair_elect(empty_a(sa)); else umma_commit_elect(empty_a(sa));
           if (++sa == p.na) { sa = 0; pha ^= 1; }
         }
-        if (CTAS == 2) umma_commit_pair_elect(acc_full(set)); else umma_commit_elect(acc_full(set));
       }
     }
   } else if (warp >= 4) {
@@ -332,7 +344,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       __half* ppx0 = p.pool_out ? p.pool_out + (((size_t)img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
                                                    (size_t)p.pool_ctot
                                 : nullptr;
-      if (p.probe == 2) continue;
+      if ((p.probe & 3) == 2) continue;
 #pragma unroll
       for (int c = 0; c < kCols; c += 8) {
         float v[8];
@@ -341,7 +353,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           v[e] = fmaf(acc[c + e], scale, bias_t[col0 + c + e]);
           if (p.relu) v[e] = fmaxf(v[e], 0.f);
         }
-        if (px0 && inside && (p.probe != 1 || v[0] == 12345.678f)) act_store8(px0, (size_t)p.plane_elems, p.cout_offset + n0 + col0 + c, v, p.out_fmt);
+        if (px0 && inside && ((p.probe & 3) != 1 || v[0] == 12345.678f)) act_store8(px0, (size_t)p.plane_elems, p.cout_offset + n0 + col0 + c, v, p.out_fmt);
         if (p.pool_out) {                                   // warp-uniform branch: all lanes take part in the shuffles
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -350,7 +362,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
             v[e] = q;
           }
-          if (pool_writer && (p.probe != 1 || v[0] == 12345.678f)) act_store8(ppx0, (size_t)p.pool_plane_elems, p.pool_coffset + n0 + col0 + c, v, p.out_fmt);
+          if (pool_writer && ((p.probe & 3) != 1 || v[0] == 12345.678f)) act_store8(ppx0, (size_t)p.pool_plane_elems, p.pool_coffset + n0 + col0 + c, v, p.out_fmt);
         }
       }
     }
