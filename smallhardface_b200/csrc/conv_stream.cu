@@ -62,6 +62,96 @@ struct StreamParams {
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue store: a warp holds 32 pixels (lane = pixel) x KC channels (registers).  Written straight from registers
+// every lane would store 16-byte (h2) or 8-byte (hf8) pieces of ITS OWN pixel row: 32 partial sectors per
+// instruction, which made the LSU/L2 request rate the limiter of the short-K layers (tools/probe_epi.py).  Instead the
+// warp stages its rows -- exactly the bytes of each pixel's slice of one plane -- in 4 KB of shared memory (16-byte
+// chunks XOR-swizzled so both directions are conflict free) and copies them out with consecutive lanes on
+// consecutive 16 bytes of a row: full 32-byte sectors, 64 or 128 contiguous bytes per pixel.
+// `rows`: 32 (lane r = row r) or 8 (the fused-pool writers: row wr lives in lane ((wr >> 2) << 4) | ((wr & 3) << 1)).
+// ---------------------------------------------------------------------------------------------------------------
+template <int KC>
+struct RowStore {
+  static constexpr int kChunks = KC / 8;               // 16-byte chunks per row and plane (row = 2 * KC bytes)
+  static constexpr int kRowBytes = KC * 2;
+  SHF_DEVICE static int swz(int row, int k) { return KC == 64 ? (k ^ (row & 7)) : (k ^ ((row >> 1) & 3)); }
+  SHF_DEVICE static void put(uint8_t* stg, int row, int k, const uint4& v) {
+    *reinterpret_cast<uint4*>(stg + row * kRowBytes + swz(row, k) * 16) = v;
+  }
+  SHF_DEVICE static uint4 get(const uint8_t* stg, int row, int k) {
+    return *reinterpret_cast<const uint4*>(stg + row * kRowBytes + swz(row, k) * 16);
+  }
+};
+
+// Stage one plane of `v` (KC final values of this lane's pixel) and copy it out.  dst_px(row) must return the plane-0
+// address of channel 0 of that row's pixel, or nullptr when the row is outside the image / not a writer.
+template <int KC, typename DstFn>
+SHF_DEVICE void store_plane(uint8_t* stg, int lane, bool lane_writes, int lane_row, int nrows, const float (&v)[KC], int plane,
+                            int fmt, int c_first, size_t plane_elems, DstFn dst_px) {
+  using RS = RowStore<KC>;
+  if (lane_writes) {
+    if (plane == 0 || fmt == SHF_FMT_H2) {
+#pragma unroll
+      for (int k = 0; k < KC / 8; ++k) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = v[8 * k + 2 * e], b = v[8 * k + 2 * e + 1];
+          __half2 h = __floats2half2_rn(a, b);
+          if (plane == 1) {                                  // h2 lo plane: rn16(x - hi)
+            const float2 hf = __half22float2(h);
+            h = __floats2half2_rn(a - hf.x, b - hf.y);
+          }
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        RS::put(stg, lane_row, k, make_uint4(w[0], w[1], w[2], w[3]));
+      }
+    } else {                                                 // hf8 plane 1: [KC x e5m2((x - hi) * 2^10) | KC x e5m2(hi)]
+#pragma unroll
+      for (int k = 0; k < KC / 16; ++k) {
+        uint32_t wa[4], wb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t a4 = 0u, b4 = 0u;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float a = v[16 * k + 4 * e + 2 * q], b = v[16 * k + 4 * e + 2 * q + 1];
+            const float2 hf = __half22float2(__floats2half2_rn(a, b));
+            const float2 lo = make_float2((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
+            a4 |= (uint32_t)__nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E5M2) << (16 * q);
+            b4 |= (uint32_t)__nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E5M2) << (16 * q);
+          }
+          wa[e] = a4;
+          wb[e] = b4;
+        }
+        RS::put(stg, lane_row, k, make_uint4(wa[0], wa[1], wa[2], wa[3]));
+        RS::put(stg, lane_row, KC / 16 + k, make_uint4(wb[0], wb[1], wb[2], wb[3]));
+      }
+    }
+  }
+  __syncwarp();
+  const int items = nrows * RS::kChunks;
+  for (int i = lane; i < items; i += 32) {
+    const int row = i / RS::kChunks, k = i % RS::kChunks;
+    __half* px = dst_px(row);
+    if (px == nullptr) continue;
+    const int srow = (nrows == 32) ? row : (((row >> 2) << 4) | ((row & 3) << 1));
+    const uint4 val = RS::get(stg, srow, k);
+    if (plane == 0) {
+      *reinterpret_cast<uint4*>(px + c_first + 8 * k) = val;
+    } else if (fmt == SHF_FMT_H2) {
+      *reinterpret_cast<uint4*>(px + plane_elems + c_first + 8 * k) = val;
+    } else {
+      // chunks [0, KC/16) are al8 of channels c_first + 16k .., chunks [KC/16, KC/8) their ah8 twins 64 bytes further
+      const int half = k / (KC / 16), kk = k % (KC / 16);
+      uint8_t* p1 = reinterpret_cast<uint8_t*>(px + plane_elems) + hf8_off(c_first) + half * 64 + kk * 16;
+      *reinterpret_cast<uint4*>(p1) = val;
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -74,6 +164,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t bar_base = smem_base + (uint32_t)pipe_bytes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pipe_bytes + 8 * (2 * kMaxA + 2 * kMaxB + 4));
   float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 512);      // [2][BN]: this tile's bias slice, double-buffered
+  uint8_t* stage_s = smem + pipe_bytes + 1536;                            // 8 x 4 KB: row staging of the epilogue warps
   auto full_a = [&](int s) { return bar_base + 8u * s; };
   auto empty_a = [&](int s) { return bar_base + 8u * (kMaxA + s); };
   auto full_b = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
@@ -338,31 +429,45 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < p.H && x < p.W);
       const int n0 = nt * BN;
-      // plane-0 address of channel 0 of this thread's pixel (and of its pooled pixel)
-      __half* px0 = p.out ? p.out + (((size_t)img * p.H + y) * p.W + x) * (size_t)p.ctot : nullptr;
       const bool pool_writer = p.pool_out && inside && !(lane & 9);        // lane bits 0 (x) and 3 (y) clear: window origin
-      __half* ppx0 = p.pool_out ? p.pool_out + (((size_t)img * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
-                                                   (size_t)p.pool_ctot
-                                : nullptr;
       if ((p.probe & 3) == 2) continue;
 #pragma unroll
-      for (int c = 0; c < kCols; c += 8) {
-        float v[8];
+      for (int c = 0; c < kCols; ++c) {
+        acc[c] = fmaf(acc[c], scale, bias_t[col0 + c]);
+        if (p.relu) acc[c] = fmaxf(acc[c], 0.f);
+      }
+      uint8_t* stg = stage_s + w * 4096;
+      const int c_first = n0 + col0;
+      if (p.out && (p.probe & 3) != 1) {
+        const int qy = y0 + quad * 4;                       // this warp's 4 x 8 pixel patch
+        auto dst = [&](int row) -> __half* {
+          const int yy = qy + (row >> 3), xx = x0 + (row & 7);
+          return (yy < p.H && xx < p.W) ? p.out + (((size_t)img * p.H + yy) * p.W + xx) * (size_t)p.ctot : nullptr;
+        };
+        store_plane<kCols>(stg, lane, true, lane, 32, acc, 0, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
+        store_plane<kCols>(stg, lane, true, lane, 32, acc, 1, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
+      }
+      if (p.pool_out) {                                     // warp-uniform branch: all lanes take part in the shuffles
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[e] = fmaf(acc[c + e], scale, bias_t[col0 + c + e]);
-          if (p.relu) v[e] = fmaxf(v[e], 0.f);
+        for (int c = 0; c < kCols; ++c) {
+          float q = inside ? acc[c] : -3.402823466e38f;
+          q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
+          q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
+          acc[c] = q;
         }
-        if (px0 && inside && ((p.probe & 3) != 1 || v[0] == 12345.678f)) act_store8(px0, (size_t)p.plane_elems, p.cout_offset + n0 + col0 + c, v, p.out_fmt);
-        if (p.pool_out) {                                   // warp-uniform branch: all lanes take part in the shuffles
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float q = inside ? v[e] : -3.402823466e38f;
-            q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
-            q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
-            v[e] = q;
-          }
-          if (pool_writer && ((p.probe & 3) != 1 || v[0] == 12345.678f)) act_store8(ppx0, (size_t)p.pool_plane_elems, p.pool_coffset + n0 + col0 + c, v, p.out_fmt);
+        if ((p.probe & 3) != 1) {
+          const int qy = y0 + quad * 4;
+          const int ph2 = p.H >> 1, pw2 = p.W >> 1;
+          auto dst = [&](int row) -> __half* {              // row = pooled pixel (2 rows x 4 columns per warp)
+            const int yy = qy + ((row >> 2) << 1), xx = x0 + ((row & 3) << 1);
+            return (yy < p.H && xx < p.W)
+                       ? p.pool_out + (((size_t)img * ph2 + (yy >> 1)) * pw2 + (xx >> 1)) * (size_t)p.pool_ctot
+                       : nullptr;
+          };
+          store_plane<kCols>(stg, lane, pool_writer, lane, 8, acc, 0, p.out_fmt, p.pool_coffset + c_first,
+                             (size_t)p.pool_plane_elems, dst);
+          store_plane<kCols>(stg, lane, pool_writer, lane, 8, acc, 1, p.out_fmt, p.pool_coffset + c_first,
+                             (size_t)p.pool_plane_elems, dst);
         }
       }
     }
@@ -453,7 +558,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.a_tx = 2 * p.xh * p.xw * 128;
   p.a_bytes = (p.a_tx + 1023) & ~1023;
   p.b_bytes = 2 * (bn / ctas) * 128;          // per CTA: its share of the output channels, hi + lo plane
-  const int budget = 227 * 1024 - 1024 - 1536;      // alignment slack; barriers (512) + staged bias (1024)
+  const int budget = 227 * 1024 - 1024 - 1536 - 8 * 4096;      // alignment slack; barriers (512) + staged bias (1024); epilogue row staging
   // A-ring depth: a halo stage lasts taps x 4 k-steps of MMAs; when that is short (one 64-channel chunk per tile at
   // BN = 64: ~2-3k cycles, or 1x1 convs) two stages do not cover the ~4k cycles a 46 KB halo takes to arrive
   p.na = (p.taps == 1) ? kMaxA : ((bn == 64 || p.cin_chunks == 1) ? 3 : 2);
@@ -488,7 +593,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.pool_plane_elems = (long long)batch * (H / 2) * (W / 2) * pool_channels_total;
   p.pool_ctot = pool_channels_total;
   p.pool_coffset = pool_channel_offset;
-  const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 1536;
+  const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 1536 + 8 * 4096;
 
   CUtensorMap ta, tb;
   {
