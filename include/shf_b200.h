@@ -61,6 +61,13 @@ int shf_set_conv_impl(int impl);
 int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, void* out_h2, int batch, int H, int W,
                  int cout, int relu, int out_format, void* stream);
 
+/* conv1_1 on the tensor cores (the product path; shf_conv1_c3 is the fp32 SIMT twin kept for validation): the 27 taps of
+ * a pixel form one split-fp16 K-major operand row built in shared memory, six tcgen05 MMAs per 128-pixel tile.
+ * w_packed [dev]: fp16 [2][64][64] of (w * 2^k): [0] = rows [hi(32) | hi(32)], [1] = rows [lo(32) | 0], K index
+ * c*9 + r*3 + s padded to 32; out_scale = 2^-k. */
+int shf_conv1_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H, int W,
+                 int cout, float out_scale, int relu, int out_format, void* stream);
+
 /* PoolingLayer MAX 2x2 stride 2 (pooling_layer.cpp:79-123,140-187), ceil-mode output (H+1)/2 x (W+1)/2. */
 int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, int format, void* stream);
 

@@ -93,6 +93,24 @@ def pack_conv_weights_hf8(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
     return np.stack([hi_l, plane1.view(np.float16)]), k
 
 
+def pack_conv1_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
+    """(64, 3, 3, 3) fp32 -> fp16 [2][64][64] for ``shf_conv1_tc``: row n of [0] = [hi(k) | hi(k)], of [1] = [lo(k) | 0]
+    with k = c*9 + r*3 + s padded from 27 to 32, hi/lo the split-fp16 parts of w * 2^k'; returns (packed, k')."""
+    w = np.asarray(w_oihw, dtype=np.float32)
+    co = w.shape[0]
+    if w.shape[1:] != (3, 3, 3):
+        raise ValueError("conv1 weights must be (Cout, 3, 3, 3)")
+    amax = float(np.abs(w).max())
+    k = 0 if amax == 0 or not np.isfinite(amax) else int(14 - math.ceil(math.log2(amax)))
+    k = max(-14, min(k, 24))
+    hi, lo = split_h2_np(w.reshape(co, 27) * np.float32(2.0 ** k))
+    out = np.zeros((2, co, 64), dtype=np.float16)
+    out[0, :, :27] = hi
+    out[0, :, 32:59] = hi
+    out[1, :, :27] = lo
+    return out, k
+
+
 FMT_H2, FMT_HF8 = L.FMT_H2, L.FMT_HF8
 
 
@@ -245,6 +263,9 @@ class GpuNet:
                     if not (p["kh"] == 3 and p["ph"] == 1 and p["dh"] == 1 and p["num_output"] == 64):
                         raise L.ShfError("conv %s: 3-channel convs must be 3x3 pad 1 with 64 outputs" % l.name)
                     st["w"] = torch.from_numpy(np.ascontiguousarray(w, F32)).to(dev)
+                    packed1, k1 = pack_conv1_weights(w)
+                    st["wtc"] = torch.from_numpy(packed1).to(dev)
+                    st["scale"] = float(2.0 ** (-k1))
                     self.ops.append(("conv1", l, st))
                 else:
                     if p["kh"] not in (1, 3) or (p["kh"] == 3 and p["ph"] != p["dh"]) or (p["kh"] == 1 and p["ph"] != 0):
@@ -407,8 +428,8 @@ class GpuNet:
             if kind == "conv1":
                 n, _, h, w = x.shape
                 out = self._alloc_out(l.tops[0], n, h, w, s["cout"], fmt)
-                L.call("shf_conv1_c3", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
-                       int(s["relu"]), out.fmt, st)
+                L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
+                       s["scale"], int(s["relu"]), out.fmt, st)
             elif kind == "conv":
                 if x.c_off != 0 or x.c != x.ctot:
                     raise L.ShfError("conv %s reads a channel window; not supported" % l.name)

@@ -30,6 +30,8 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "shf_set_conv_impl": (c_int, [c_int]),
     "shf_conv1_c3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "shf_conv1_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+                             c_void_p]),
     "shf_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_deconv_depthwise": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p]),

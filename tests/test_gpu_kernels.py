@@ -76,6 +76,26 @@ def test_conv1_c3_matches_oracle():
     assert relerr(got, ref) < 2e-6
 
 
+@pytest.mark.parametrize("H,W,fmt", [(37, 53, 0), (16, 8, 0), (40, 24, 1), (5, 3, 0)])
+def test_conv1_tensor_core_matches_oracle(H, W, fmt):
+    """conv1_1 as six tcgen05 MMAs per tile (the product path) vs the oracle and vs its SIMT twin."""
+    from smallhardface_b200.engine import pack_conv1_weights
+    rng = np.random.RandomState(H + W)
+    x = (rng.rand(2, 3, H, W) * 255 - 110).astype(F32)
+    w = (rng.randn(64, 3, 3, 3) * 0.27).astype(F32)
+    b = (rng.randn(64) * 0.05).astype(F32)
+    packed, k = pack_conv1_weights(w)
+    out = H2(torch.zeros((2, 2, H, W, 64), dtype=torch.float16, device=DEV), fmt=fmt)
+    L.call("shf_conv1_tc", _ptr(dev(x)), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), 2, H, W, 64, float(2.0 ** -k), 1, fmt,
+           _stream())
+    got = out.to_nchw().cpu().numpy()
+    ref = OL.relu(OL.conv(x, w, b, pad=(1, 1)))
+    assert relerr(got, ref) < (2e-6 if fmt == 0 else 2 ** -14)
+    simt = H2.empty(2, H, W, 64, DEV, fmt=fmt)
+    L.call("shf_conv1_c3", _ptr(dev(x)), _ptr(dev(w)), _ptr(dev(b)), _ptr(simt.t), 2, H, W, 64, 1, fmt, _stream())
+    assert relerr(got, simt.to_nchw().cpu().numpy()) < (2e-6 if fmt == 0 else 2 ** -13)
+
+
 CONV_CASES = [
     # cin, cout, H, W, k, dil, ctot, coff, relu
     (64, 64, 24, 40, 3, 1, 64, 0, 1),
