@@ -243,16 +243,19 @@ def run_ours(args):
     n_conv = len(det.net.events)
     det.net.events = []
     # e2e: same steps through the public API with host images
-    for _ in range(min(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
     n_out = 0
-    for _ in range(args.steps):
-        res = step_e2e()
-        n_out = sum(r.nbytes for r in res)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    if args.no_e2e:
+        e2e_s = float("nan")
+    else:
+        for _ in range(min(args.warmup, 3)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step_e2e()
+            n_out = sum(r.nbytes for r in res)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,6 +307,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

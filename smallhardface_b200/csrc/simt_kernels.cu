@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restr
 __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                                __half* __restrict__ out, int N, int H, int W, int C,
                                                                int CT, int c_off, int in_fmt, int out_fmt) {
-  extern __shared__ float wsm[];                 // [C][16]
-  for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[i] = w[i];
+  extern __shared__ float wsm[];                 // [16 taps][C]: a warp's lanes (consecutive 8-channel groups) read
+                                                 // consecutive 32-byte runs (the [C][16] layout was a 32-way bank conflict)
+  for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[(i & 15) * C + (i >> 4)] = w[i];
   __syncthreads();
   const int HO = 2 * H, WO = 2 * W, cv = C / 8;
   const long long total = (long long)N * HO * WO * cv;
@@ -220,8 +221,10 @@ __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __r
         if (ox + 1 - kx < 0 || ix >= W) continue;
         float v[8];
         act_load8(in + (((size_t)n * H + iy) * W + ix) * C, in_plane, c8 * 8, v, in_fmt);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += v[j] * wsm[(c8 * 8 + j) * 16 + ky * 4 + kx];
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 4 + kx) * C + c8 * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 4 + kx) * C + c8 * 8 + 4);
+        acc[0] += v[0] * w0.x; acc[1] += v[1] * w0.y; acc[2] += v[2] * w0.z; acc[3] += v[3] * w0.w;
+        acc[4] += v[4] * w1.x; acc[5] += v[5] * w1.y; acc[6] += v[6] * w1.z; acc[7] += v[7] * w1.w;
       }
     }
     act_store8(out + (((size_t)n * HO + oy) * WO + ox) * CT, out_plane, c_off + c8 * 8, acc, out_fmt);

@@ -1,0 +1,85 @@
+"""Turns gpurun_out/launches_*.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_*.sum --csv) and .ncu-rep captures
+into the tracked summaries under profiles/.  Runs here (no GPU): `python tools/summarize_profiles.py <tag>`."""
+import csv, json, re, subprocess, sys, os
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+go, prof = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    L = {}
+    for r in rows[hi + 2:]:
+        if len(r) <= iv: continue
+        d = L.setdefault(int(r[iid]), {"k": r[ik]})
+        d[r[im]] = float(r[iv].replace(",", ""))
+    return [L[i] for i in sorted(L)]
+
+def short(k):
+    k = re.sub(r"^void ", "", k)
+    k = re.sub(r"<unnamed>::", "", k)
+    m = re.match(r"([\w:]+(?:<[^(]*?>)?)", k)
+    return (m.group(1) if m else k)[:70]
+
+src = os.path.join(go, "launches_%s.csv" % tag)
+if os.path.exists(src):
+    L = launches(src)
+    n = len(L)
+    step = L[n // 2:]                               # second half = the timed step (first half = its warm-up twin)
+    tot = sum(d["gpu__time_duration.sum"] for d in step)
+    agg = {}
+    for d in step:
+        a = agg.setdefault(short(d["k"]), [0, 0.0, 0.0])
+        a[0] += 1; a[1] += d["gpu__time_duration.sum"]
+        a[2] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+    with open(os.path.join(prof, "%s_launches_bench_step.csv" % tag), "w") as f:
+        f.write("id,kernel,gpu__time_duration_us,dram_read_bytes,dram_write_bytes\n")
+        for i, d in enumerate(step):
+            f.write('%d,"%s",%.2f,%d,%d\n' % (i, short(d["k"]), d["gpu__time_duration.sum"] / 1e3,
+                                               d.get("dram__bytes_read.sum", 0), d.get("dram__bytes_write.sum", 0)))
+    conv = [d for d in step if "conv_stream" in d["k"]]
+    conv_t = sum(d["gpu__time_duration.sum"] for d in conv)
+    conv_b = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in conv)
+    with open(os.path.join(prof, "%s_launches_summary.md" % tag), "w") as f:
+        f.write("# %s -- ncu launch list of one `bench.py` step\n\n" % tag)
+        f.write("Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+                "--csv --log-file gpurun_out/launches_%s.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e` "
+                "(second of the two captured steps; 8 images x 5 pyramid levels x {plain, mirrored}, batched 16 per level). "
+                "Serialised, cold-cache durations: read SHARES. Per-launch rows: `%s_launches_bench_step.csv`.\n\n" % (tag, tag))
+        f.write("| kernel | launches | total ms | share | avg us | DRAM GB (rd+wr) |\n|---|---:|---:|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| `%s` | %d | %.2f | %.1f%% | %.1f | %.2f |\n" % (k, a[0], a[1] / 1e6, 100 * a[1] / tot, a[1] / a[0] / 1e3, a[2] / 1e9))
+        f.write("\nTotal %.1f ms GPU time for the step. tcgen05 conv (`conv_stream_kernel`) share: **%.1f%%**; "
+                "DRAM traffic of its %d launches: %.1f GB = **%.1f MB per launch** on average.\n"
+                % (tot / 1e6, 100 * conv_t / tot, len(conv), conv_b / 1e9, conv_b / len(conv) / 1e6))
+    json.dump({"conv_launches": len(conv), "conv_dram_bytes_per_launch": conv_b / len(conv), "conv_share_of_step": conv_t / tot,
+               "source": "profiles/%s_launches_summary.md (ncu launch list, one bench step)" % tag},
+              open(os.path.join(prof, "%s_conv_traffic.json" % tag), "w"), indent=1)
+    print(open(os.path.join(prof, "%s_launches_summary.md" % tag)).read())
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "launch__cluster_size", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
+out = []
+for rep in sorted(os.listdir(go)):
+    if not (rep.startswith(tag) and rep.endswith(".ncu-rep")): continue
+    r = subprocess.run(["ncu", "-i", os.path.join(go, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
+    rows = list(csv.reader(r.stdout.splitlines()))
+    if len(rows) < 3: continue
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    out.append((rep, d))
+if out:
+    with open(os.path.join(prof, "%s_ncu_full.md" % tag), "w") as f:
+        f.write("# %s -- `ncu --set full --clock-control none --import-source on` captures (one launch each)\n\n" % tag)
+        f.write("Commands: `ncu --set full --clock-control none --import-source on -k regex:conv_stream -s 2 -c 1 -o gpurun_out/<name> "
+                "python tools/ncu_one.py 8 512 512 256 256 3 1 <fmt>` (the conv4_2-class shape of the 2048-px level: 512->512 3x3 at "
+                "256x256; fmt 0 = split fp16, 1 = fp16 + fp8) and the same for `conv1_tc` (3->64 at 2048x2048).\n\n")
+        f.write("| capture | " + " | ".join(k.replace("_", "\\_") for k in KEYS) + " |\n|---|" + "---:|" * len(KEYS) + "\n")
+        for rep, d in out:
+            f.write("| %s | " % rep + " | ".join("%s %s" % (d.get(k, ("", ""))[0], d.get(k, ("", ""))[1]) for k in KEYS) + " |\n")
+    print(open(os.path.join(prof, "%s_ncu_full.md" % tag)).read()[:3000])
