@@ -104,6 +104,42 @@ def deploy_dir():
     return os.path.join(tempfile.gettempdir(), "shf_b200_deploy")
 
 
+def conv_traffic():
+    """DRAM bytes per tcgen05 conv launch from the committed ncu launch list of this same command
+    (profiles/*_conv_traffic.json, written by tools/summarize_profiles.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    return float(d["conv_dram_bytes_per_launch"]), d.get("source")
+
+
+def conv_bytes_per_image(det, hw):
+    """Algorithmic bytes of the same launches: 4 B per activation element in and out + the packed weights."""
+    from smallhardface_b200.detector import level_geometry, pyramid_scales
+    spec = det.net.spec
+    total, launches = 0.0, 0
+    for s in pyramid_scales(hw + (3,), det.cfg):
+        _, _, hp, wp = level_geometry(hw[0], hw[1], s, det.cfg.max_resolution)
+        shapes = spec.infer_shapes({"data": (1, 3, hp, wp)})
+        for kind, l, st in det.net.ops:
+            if kind == "conv":
+                _, ci, hi, wi = shapes[l.bottoms[0]]
+                out_elems = 0
+                if "pool_top" in st:
+                    _, co, ho, wo = shapes[st["pool_top"]]
+                    out_elems += co * ho * wo
+                if "pool_top" not in st or st.get("write_full"):
+                    _, co, ho, wo = shapes[l.tops[0]]
+                    out_elems += co * ho * wo
+                total += 4.0 * (ci * hi * wi + out_elems)
+                launches += 1
+    nf = 2 if det.cfg.flip else 1
+    return total * nf, launches
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -213,6 +249,7 @@ def run_ours(args):
     def step_resident():
         b = det.detect_device(dev_imgs)
         if world > 1:
+            det.wait_results(b)
             gather_detections(b["out_dets"], b["out_count"], world)      # the one collective: all-gather of boxes
         return b
 
@@ -232,7 +269,8 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        step_resident()
+        last = step_resident()
+    det.wait_results(last)            # the timed region ends after the last step's box voting (side stream)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -265,6 +303,9 @@ def run_ours(args):
         flops_img, issued_img = conv_flops_per_image(det, IMAGE_HW)
         conv_flops = flops_img * BATCH * args.steps
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic, traffic_src = conv_traffic()
+        bytes_img, launches_per_pass_set = conv_bytes_per_image(det, IMAGE_HW)
+        alg_bytes_per_launch = bytes_img * BATCH / max(1, n_conv // max(1, args.steps))
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         value = world * BATCH * args.steps / (ms * 1e-3)
         line = {
@@ -289,7 +330,10 @@ def run_ours(args):
                                  "the tensor pipe issues 2 MMAs per algorithmic MAC on the f16+f8 format (3 on split "
                                  "f16), each taking the time of one f16 MMA: issued_mma_tflops_f16_equiv is the pipe's "
                                  "own load against the same peak",
-                         "conv_share_of_step": conv_ms / ms if ms > 0 else None, "traffic": None},
+                         "conv_share_of_step": conv_ms / ms if ms > 0 else None,
+                         "avg_launch_ms": conv_ms / max(1, n_conv),
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per conv launch (average over the step's launches)",
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch},
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -303,7 +347,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -82,6 +82,8 @@ class Detector:
                           fast_min_scale=self.cfg.fast_min_scale)
         self._means = (C.c_double * 3)(*self.cfg.pixel_means)
         self._bufs = {}
+        self._flip = 0
+        self._post_stream = None             # box voting / NMS of call i overlaps the conv stack of call i+1
         self.max_batch_bytes = 40e9          # activation budget used to size per-level batches (180 GB HBM per GPU)
 
     # ------------------------------------------------------------------------------------------
@@ -96,7 +98,10 @@ class Detector:
         return out
 
     def _buffers(self, batch: int, passes: int):
-        key = (batch, passes)
+        # two buffer sets used alternately: the post-processing of one call (side stream, one CTA per image -- it would
+        # leave 140 SMs idle on the main stream) may still be running when the next call starts filling the other set
+        self._flip ^= 1
+        key = (batch, passes, self._flip)
         b = self._bufs.get(key)
         if b is None:
             cap = passes * self.net.cfg["pre_nms_topn"]
@@ -128,7 +133,9 @@ class Detector:
 
     def detect_device(self, dev_images: List[torch.Tensor]):
         """Runs the whole pipeline for a batch of device-resident images; returns the device buffers
-        (out_dets (B,max,5), out_idx (B,max), out_count (B,), dets (B,cap,5)) without synchronising.
+        (out_dets (B,max,5), out_idx (B,max), out_count (B,), dets (B,cap,5)) without synchronising.  The final
+        vote / NMS launch is queued on a side stream: ``wait_results(b)`` (or ``download``) orders a consumer after it.
+        A returned set stays valid until the second-next call with the same batch shape.
 
         Same-sized images are stacked per pyramid level together with their mirrored copies, so the conv stack
         sees N = images x flips per launch (the small levels would not fill 148 SMs otherwise); the
@@ -141,6 +148,8 @@ class Detector:
         passes = nscales * nf
         B = len(dev_images)
         b = self._buffers(B, passes)
+        if b.get("done") is not None:
+            torch.cuda.current_stream().wait_event(b["done"])      # this set's previous post-processing has finished
         b["offs"].zero_()
         groups = {}
         for i, img in enumerate(dev_images):
@@ -165,19 +174,35 @@ class Detector:
                     self.net.forward_body(data, fast=self.net.use_fast(s))
                     self.net.run_tail_batched(nf, info, b["dets"], b["offs"], image_base=sub[0], passes_total=passes,
                                               pass_base=li * nf, det_cap=b["cap"], det_thresh=cfg.thresh)
-        torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])
         method = 1 if cfg.nms_method == "BBOX_VOTE" else 0
         if cfg.nms_method not in ("BBOX_VOTE", "NMS"):
             raise NotImplementedError("Unknown NMS method: {}".format(cfg.nms_method))     # lib/test.py:173-175
-        L.call("shf_postprocess", _ptr(b["dets"]), _ptr(b["seg_begin"]), _ptr(b["seg_end"]), B, b["cap"],
-               float(cfg.nms_thresh), method, int(cfg.nms_mode), _ptr(b["out_idx"]), _ptr(b["out_dets"]),
-               _ptr(b["out_count"]), cfg.max_dets_out, _ptr(b["ws"]), b["ws_bytes"], _stream())
+        if self._post_stream is None:
+            self._post_stream = torch.cuda.Stream(device=self.device)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self._post_stream):
+            self._post_stream.wait_event(ready)
+            torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])
+            L.call("shf_postprocess", _ptr(b["dets"]), _ptr(b["seg_begin"]), _ptr(b["seg_end"]), B, b["cap"],
+                   float(cfg.nms_thresh), method, int(cfg.nms_mode), _ptr(b["out_idx"]), _ptr(b["out_dets"]),
+                   _ptr(b["out_count"]), cfg.max_dets_out, _ptr(b["ws"]), b["ws_bytes"], _stream())
+            done = torch.cuda.Event()
+            done.record()
+        b["done"] = done
         self.net.launches += 3 + B
         return b
+
+    def wait_results(self, b):
+        """Orders the current stream after the post-processing of ``b`` (call before reading out_dets / out_idx /
+        out_count on the device; ``download`` does it itself)."""
+        if b.get("done") is not None:
+            torch.cuda.current_stream().wait_event(b["done"])
 
     def download(self, b, B: int) -> List[np.ndarray]:
         """Device results -> list of (M,5) arrays ``[x1,y1,x2,y2,score]`` (float64 for BBOX_VOTE, as
         ``bbox_vote`` returns; float32 rows of ``dets`` for NMS)."""
+        self.wait_results(b)
         counts = b["out_count"][:B].cpu().numpy()
         slots = []
         if self.cfg.nms_method == "BBOX_VOTE":
