@@ -91,6 +91,39 @@ def test_weight_packing_is_exact_to_22_bits():
     assert np.isfinite(packed.astype(np.float32)).all()
 
 
+def test_fast_format_weight_packing_layout_and_precision():
+    """hf8 weights: plane 0 = fp16 hi of w*2^k; plane 1 = per (tap, Cout, 64-channel block) 64 bytes e4m3(hi*2^-10) then
+    64 bytes e4m3(lo).  hi + lo8 reconstructs w to ~2^-15; the 8-bit hi copy is the 4-bit-mantissa image of hi."""
+    import torch
+    from smallhardface_b200.engine import pack_conv_weights, pack_conv_weights_hf8
+    rng = np.random.RandomState(5)
+    w = (rng.randn(128, 192, 3, 3) * 0.03).astype(np.float32)
+    p8, k8 = pack_conv_weights_hf8(w)
+    p2, k2 = pack_conv_weights(w)
+    assert k8 == k2 and p8.dtype == np.float16 and p8.shape == (2, 9, 128, 192)
+    assert np.array_equal(p8[0], p2[0])                              # same fp16 hi plane as the precise format
+    f8 = torch.from_numpy(p8[1].view(np.uint8).copy()).view(torch.float8_e4m3fn).to(torch.float32).numpy()
+    f8 = f8.reshape(9, 128, 3, 2, 64)
+    hi8 = f8[:, :, :, 0].reshape(9, 128, 192) * 1024.0
+    lo8 = f8[:, :, :, 1].reshape(9, 128, 192)
+    hi = p8[0].astype(np.float32)
+    ws = w.transpose(2, 3, 0, 1).reshape(9, 128, 192) * np.float32(2.0 ** k8)
+    assert np.abs(hi8 - hi).max() <= np.abs(hi).max() * 2.0 ** -4           # e4m3: 3 mantissa bits + rounding
+    assert np.abs(hi + lo8 - ws).max() <= np.abs(ws).max() * 2.0 ** -15
+    assert np.abs(hi - ws).max() > np.abs(hi + lo8 - ws).max() * 4           # the 8-bit lo really refines hi
+
+
+def test_conv1_tensor_core_weight_packing():
+    from smallhardface_b200.engine import pack_conv1_weights
+    w = (np.random.RandomState(6).randn(64, 3, 3, 3) * 0.27).astype(np.float32)
+    p, k = pack_conv1_weights(w)
+    assert p.shape == (2, 64, 64) and p.dtype == np.float16
+    hi, lo = p[0].astype(np.float64), p[1].astype(np.float64)
+    assert np.array_equal(hi[:, :27], hi[:, 32:59]) and not hi[:, 27:32].any() and not hi[:, 59:].any() and not lo[:, 27:].any()
+    rec = (hi[:, :27] + lo[:, :27]) * 2.0 ** -k
+    assert np.abs(rec - w.reshape(64, 27)).max() <= np.abs(w).max() * 2.0 ** -21
+
+
 # ---- caffe / caffe_pb2 shims ---------------------------------------------------------------------
 def test_caffe_pb2_shim_text_and_wire():
     from smallhardface_b200 import compat
