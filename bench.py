@@ -217,6 +217,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def plugin_path_sample(proto, model, image, cfg, reps=2):
+    """The reference-facing drop-in surface, driven the way lib/test.py:109-158 drives pycaffe: host mean-subtract +
+    cv2.resize per pyramid level (test_utils.py:29-46), zero pad, `net.blobs[..].reshape`, `net.forward(data=, im_info=)`
+    with HOST float32 blobs for the plain and the mirrored pass, `.data` reads of boxes / cls_prob.  One image at a time,
+    batch 1 per forward (the ProposalLayer contract, proposal_layer.py:74-75); the reference's NumPy bbox_vote that
+    follows is not part of the replaced surface and is not timed.  Returns images/s."""
+    import cv2
+    from smallhardface_b200 import compat
+    from smallhardface_b200.detector import pyramid_scales
+    compat.install()
+    import caffe
+    caffe.set_mode_gpu()
+    caffe.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    net = caffe.Net(proto, model, caffe.TEST)
+    means = np.array([[cfg.pixel_means]], dtype=np.float32)
+    scales = pyramid_scales(image.shape, cfg)
+
+    def one_image():
+        im_copy = image.astype(np.float32, copy=True) - means
+        rows = 0
+        for s in scales:
+            lvl = im_copy if s == 1.0 else cv2.resize(im_copy, None, None, fx=s, fy=s, interpolation=cv2.INTER_LINEAR)
+            blob = np.ascontiguousarray(lvl.transpose(2, 0, 1)[None])
+            for flip in (False, True) if cfg.flip else (False,):
+                d = np.ascontiguousarray(blob[..., ::-1]) if flip else blob
+                h, w = d.shape[2:]
+                nh, nw = -(-h // 16) * 16, -(-w // 16) * 16
+                data = np.pad(d, ((0, 0), (0, 0), (0, nh - h), (0, nw - w)), "constant")
+                info = np.array([[h, w, s]], dtype=np.float32)
+                net.blobs["data"].reshape(*data.shape)
+                net.blobs["im_info"].reshape(*info.shape)
+                out = net.forward(data=data, im_info=info)
+                if flip:
+                    out["boxes"][:, [1, 3]] = w - out["boxes"][:, [3, 1]]
+                rows += (net.blobs["boxes"].data[:, 1:5] / s).shape[0] + net.blobs["cls_prob"].data.shape[0]
+        return rows
+
+    one_image()                                     # warm-up: allocations, tensor maps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_image()
+    return reps / (time.perf_counter() - t0)
+
+
 # -------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -335,6 +379,16 @@ def run_ours(args):
                          "traffic": traffic, "traffic_unit": "DRAM bytes per conv launch (average over the step's launches)",
                          "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes_per_launch},
         }
+        if not args.no_e2e and world == 1:
+            try:
+                ips = plugin_path_sample(proto, model, imgs[0], det.cfg)
+                line["e2e_plugin"] = {"value": ips, "unit": "images/s",
+                                      "path": "caffe.Net.forward(data=host fp32 blob) x 10 passes per image as lib/test.py drives "
+                                              "pycaffe (host cv2 resize, batch 1 per forward, boxes read back per pass); one image "
+                                              "at a time, no level batching -- the drop-in surface, not the batched Detector API "
+                                              "that `e2e` measures"}
+            except Exception as e:                   # the supplementary leg must never take the headline line down
+                line["e2e_plugin"] = {"error": repr(e)[:200]}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ips, desc, dt = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2))

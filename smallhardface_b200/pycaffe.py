@@ -70,10 +70,24 @@ def _hot_path_cfg():
 class Blob(object):
     """``caffe.Blob`` look-alike: shape bookkeeping + a host mirror exposed through ``.data``."""
 
-    def __init__(self, net, name, shape):
+    def __init__(self, net, name, shape, pinned=False):
         self._net, self._name = net, name
-        self._host = np.zeros(tuple(int(d) for d in shape), dtype=np.float32)
+        self._pinned = bool(pinned)    # net inputs: page-locked storage, so forward() uploads straight from `.data`
+        self._cap = None               # torch storage; only ever grows (Blob::Reshape, blob.cpp:46-50)
+        self._tview = None
+        self._alloc(tuple(int(d) for d in shape))
         self._stale = False            # device copy newer than the host mirror
+
+    def _alloc(self, dims):
+        import torch
+        n = 1
+        for d in dims:
+            n *= d
+        if self._cap is None or self._cap.numel() < n:
+            pin = self._pinned and torch.cuda.is_available()
+            self._cap = torch.zeros(max(n, 1), dtype=torch.float32, pin_memory=pin)
+        self._tview = self._cap[:n].view(dims) if n else self._cap[:0].view(dims)
+        self._host = self._tview.numpy()
 
     # -- shape protocol (``_caffe.cpp:453-476``) --
     @property
@@ -102,7 +116,7 @@ class Blob(object):
         if any(d < 0 for d in dims):
             raise ValueError("blob dimensions must be non-negative")
         if dims != self._host.shape:
-            self._host = np.zeros(dims, dtype=np.float32)
+            self._alloc(dims)          # contents are unspecified after a reshape, as in Caffe (no zero fill)
         return None
 
     @property
@@ -132,7 +146,7 @@ class Net(object):
         self._engine = GpuNet(self._spec, self._params, "cuda:%d" % _state["device"],
                               fast_min_scale=_state["fast_min_scale"], **_hot_path_cfg())
         shapes = self._spec.infer_shapes({})
-        self.blobs = OrderedDict((n, Blob(self, n, shapes[n])) for n in self._spec.blob_names)
+        self.blobs = OrderedDict((n, Blob(self, n, shapes[n], pinned=n in self._spec.inputs)) for n in self._spec.blob_names)
         self.inputs = list(self._spec.inputs)
         self.outputs = list(self._spec.outputs)
         self._layer_names = [l.name for l in self._spec.layers]
@@ -165,14 +179,16 @@ class Net(object):
             # concat_layer.cpp:40-44 would fail the same way inside Caffe's Reshape
             self._spec.infer_shapes({self.inputs[0]: data_blob.shape})
         dev = self._engine.device
-        host = torch.from_numpy(data_blob._host)
-        data_dev = host.pin_memory().to(dev, non_blocking=True)
+        # `.data` of an input blob is page-locked: the upload reads it directly (valid until the sync below)
+        data_dev = data_blob._tview.to(dev, non_blocking=True)
         res = self._engine.forward(data_dev, (float(info[0]), float(info[1]), float(info[2])))
         for b in self.blobs.values():
             b._stale = True
         for name in self.inputs:
             self.blobs[name]._stale = False
-        if res is not None:
+        if res is None:
+            torch.cuda.current_stream().synchronize()          # the upload above read `.data` of the input blob
+        else:
             boxes, probs, rows = res
             R = int(rows.item())                               # the one device->host sync of the forward
             tops = self._engine.tail["tops"]
