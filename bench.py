@@ -155,7 +155,7 @@ def make_images(rank):
 
 
 # -------------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(proto, model, image, levels=(0, 1, 2), threads=None):
+def cpu_baseline_sample(proto, model, image, levels=(0, 1, 2), threads=None, engine="sgemm"):
     """Times the oracle (the reference's algorithm: im2col + OpenBLAS sgemm per conv, separate ReLU/pool
     passes, NumPy ProposalLayer, NumPy bbox_vote) on a bounded sample: pyramid levels `levels` (with flip)
     of ONE image of the batch; scales the result to images/sec by the levels' share of the per-image conv
@@ -164,7 +164,7 @@ def cpu_baseline_sample(proto, model, image, levels=(0, 1, 2), threads=None):
     from oracle import postprocess as OP
     from oracle import preprocess as PRE
     from oracle.net import OracleNet
-    onet = OracleNet(proto, model, engine="sgemm", fast=True)
+    onet = OracleNet(proto, model, engine=engine, fast=True)
     scales = PRE.pyramid_scales(image.shape)
     t0 = time.perf_counter()
     blobs = PRE.get_image_blobs(image, [scales[i] for i in levels])
@@ -392,7 +392,15 @@ def run_ours(args):
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ips, desc, dt = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2))
-            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc}
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
+                                    "algorithm": "the reference's: im2col + OpenBLAS sgemm per conv, separate ReLU / pool passes, "
+                                                 "NumPy ProposalLayer and bbox_vote (SURVEY 8d proxy i)"}
+            # SURVEY 8d proxy (ii): best-effort CPU (oneDNN direct convolutions through torch), same sample
+            import torch as _t
+            _t.set_num_threads(cores)
+            ips2, desc2, _ = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2), engine="torch")
+            line["cpu_baseline_onednn"] = {"value": ips2, "unit": "images/s", "cores": cores, "kind": "port",
+                                           "sample": desc2, "algorithm": "same layers with torch/oneDNN fp32 convolutions"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
