@@ -90,6 +90,12 @@ int shf_nchw_to_h2(const float* in_nchw, void* out_h2, int batch, int channels, 
 int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float* out_chw, int out_h, int out_w, int padded_h,
                          int padded_w, double scale, int flip, const double* means, void* stream);
 
+/* The same for num_images stacked same-sized images (N, h, w, 3) and passes in {1, 2} (plain [+ mirrored]) in ONE launch:
+ * out_nchw is the (num_images * passes, 3, padded_h, padded_w) level batch, slot j * passes + f. */
+int shf_preprocess_level_batched(const uint8_t* imgs_nhwc, int num_images, int h, int w, float* out_nchw, int out_h,
+                                 int out_w, int padded_h, int padded_w, double scale, int passes, const double* means,
+                                 void* stream);
+
 /* ---- detection tail -------------------------------------------------------------------------- */
 /* cls_score*/bbox_pred* 1x1 convs + Concat/Reshape + SoftmaxLayer (softmax_layer.cpp:27-60) + the decode half of
  * ProposalLayer.forward (lib/layers/proposal_layer.py:96-173, lib/utils/bbox_transform.py:33-93).
@@ -125,10 +131,12 @@ int shf_gather_dets_batched(const unsigned long long* sorted_keys, const int* co
                             int passes_per_image, float* dets, int* pass_offsets, int image_base, int passes_total,
                             int pass_base, int det_cap, float level_w, float im_scale, float det_thresh, void* stream);
 
-/* `max_score.argsort()[::-1]` (proposal_layer.py:181) as an ascending radix sort of the keys above
- * (ties: lower row first). */
+/* `max_score.argsort()[::-1]` (proposal_layer.py:181) as an ascending, STABLE radix sort of the keys above
+ * (ties: lower row first).  begin_bit: lowest key bit that takes part; when the keys arrive in ascending order of
+ * their row field (as shf_head_decode* writes them) pass the width of that field (32, or 27 for the batched keys) and
+ * stability orders the ties -- 0 sorts all 64 bits. */
 long long shf_sort_keys_workspace(int n);
-int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int n, void* workspace,
+int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int n, int begin_bit, void* workspace,
                   long long workspace_bytes, void* stream);
 
 /* proposal_layer.py:183-220: R = min(count, topn) rows (1 if nothing cleared the threshold) ->

@@ -577,10 +577,13 @@ extern "C" long long shf_sort_keys_workspace(int n) {
   return (long long)bytes;
 }
 
-extern "C" int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int n, void* workspace,
-                             long long workspace_bytes, void* stream) {
+extern "C" int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int n, int begin_bit,
+                             void* workspace, long long workspace_bytes, void* stream) {
+  SHF_REQUIRE(begin_bit >= 0 && begin_bit < 64, "shf_sort_keys: begin_bit %d", begin_bit);
   size_t bytes = (size_t)workspace_bytes;
-  SHF_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(workspace, bytes, keys_in, keys_out, n, 0, 64, (cudaStream_t)stream));
+  // LSD radix sort is stable: keys that arrive in ascending order of their low `begin_bit` bits (the row index) need
+  // only the bits above them sorted -- 4-5 passes instead of 8
+  SHF_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(workspace, bytes, keys_in, keys_out, n, begin_bit, 64, (cudaStream_t)stream));
   return 0;
 }
 
@@ -633,7 +636,8 @@ extern "C" int shf_postprocess(const float* dets, const int* seg_begin, const in
   for (int i = 0; i < num_images; ++i) {
     size_t b = sort_bytes;
     SHF_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(cub_tmp, b, keys_in + (size_t)i * cap_per_image,
-                                                  keys_out + (size_t)i * cap_per_image, cap_per_image, 0, 64, st));
+                                                  keys_out + (size_t)i * cap_per_image, cap_per_image, 32, 64, st));
+    // (keys are written in row order, so the stable sort only needs the 32 score bits)
   }
   if (method == 0) {
     SHF_REQUIRE(out_idx != nullptr, "shf_postprocess: NMS needs out_idx");

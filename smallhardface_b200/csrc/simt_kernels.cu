@@ -274,10 +274,9 @@ __global__ void __launch_bounds__(256) nchw_to_h2_kernel(const float* __restrict
 // Arithmetic follows oracle/preprocess.py:resize_linear: double coefficients, lerp S0+(S1-S0)*a with
 // fused multiply-add, horizontal then vertical (what opencv 4.13 computes for CV_64F).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) preprocess_level_kernel(const uint8_t* __restrict__ img, int h, int w,
-                                                               float* __restrict__ out, int oh, int ow, int HP, int WP,
-                                                               double inv_scale, int identity, int flip, double m0,
-                                                               double m1, double m2) {
+SHF_DEVICE void preprocess_level_body(const uint8_t* __restrict__ img, int h, int w, float* __restrict__ out, int oh,
+                                      int ow, int HP, int WP, double inv_scale, int identity, int flip, double m0,
+                                      double m1, double m2) {
   const long long total = (long long)HP * WP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -318,6 +317,24 @@ __global__ void __launch_bounds__(256) preprocess_level_kernel(const uint8_t* __
     out[(size_t)1 * HP * WP + i] = r1;
     out[(size_t)2 * HP * WP + i] = r2;
   }
+}
+
+__global__ void __launch_bounds__(256) preprocess_level_kernel(const uint8_t* __restrict__ img, int h, int w,
+                                                               float* __restrict__ out, int oh, int ow, int HP, int WP,
+                                                               double inv_scale, int identity, int flip, double m0,
+                                                               double m1, double m2) {
+  preprocess_level_body(img, h, w, out, oh, ow, HP, WP, inv_scale, identity, flip, m0, m1, m2);
+}
+
+// One launch for a whole level batch: blockIdx.y = slot j * passes + f of the (images x passes, 3, HP, WP) blob, image j
+// of a stacked (N, h, w, 3) uint8 tensor, pass f = 0 plain / 1 mirrored (lib/test.py:147-155).
+__global__ void __launch_bounds__(256) preprocess_level_batched_kernel(const uint8_t* __restrict__ imgs, int h, int w,
+                                                                       float* __restrict__ out, int oh, int ow, int HP,
+                                                                       int WP, double inv_scale, int identity, int passes,
+                                                                       double m0, double m1, double m2) {
+  const int slot = blockIdx.y, j = slot / passes, f = slot % passes;
+  preprocess_level_body(imgs + (size_t)j * h * w * 3, h, w, out + (size_t)slot * 3 * HP * WP, oh, ow, HP, WP, inv_scale,
+                        identity, f, m0, m1, m2);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -439,6 +456,22 @@ extern "C" int shf_preprocess_level(const uint8_t* img_hwc, int h, int w, float*
   preprocess_level_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       img_hwc, h, w, out_chw, out_h, out_w, padded_h, padded_w, 1.0 / scale, scale == 1.0 ? 1 : 0, flip, means[0],
       means[1], means[2]);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int shf_preprocess_level_batched(const uint8_t* imgs_nhwc, int num_images, int h, int w, float* out_nchw,
+                                            int out_h, int out_w, int padded_h, int padded_w, double scale, int passes,
+                                            const double* means, void* stream) {
+  SHF_REQUIRE(out_h <= padded_h && out_w <= padded_w && h > 0 && w > 0 && num_images >= 1 && (passes == 1 || passes == 2),
+              "shf_preprocess_level_batched: bad geometry");
+  const long long total = (long long)padded_h * padded_w;
+  long long gx = (total + 255) / 256;
+  if (gx > 148 * 8) gx = 148 * 8;
+  dim3 grid((unsigned)gx, (unsigned)(num_images * passes));
+  preprocess_level_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(imgs_nhwc, h, w, out_nchw, out_h, out_w, padded_h,
+                                                                         padded_w, 1.0 / scale, scale == 1.0 ? 1 : 0, passes,
+                                                                         means[0], means[1], means[2]);
   SHF_LAUNCH_CHECK();
   return 0;
 }

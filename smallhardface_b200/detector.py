@@ -118,17 +118,15 @@ class Detector:
             self._bufs[key] = b
         return b
 
-    def _level_batch(self, imgs: List[torch.Tensor], s: float, flips):
-        """One pyramid level of several same-sized images (and their mirrors) as a single (N,3,HP,WP) batch."""
-        h, w = imgs[0].shape[0], imgs[0].shape[1]
+    def _level_batch(self, stacked: torch.Tensor, s: float, flips):
+        """One pyramid level of several same-sized images (stacked (n, h, w, 3) uint8) and their mirrors as a single
+        (n * len(flips), 3, HP, WP) batch, produced by one launch."""
+        n, h, w = stacked.shape[0], stacked.shape[1], stacked.shape[2]
         oh, ow, hp, wp = level_geometry(h, w, s, self.cfg.max_resolution)
-        data = torch.empty((len(imgs) * len(flips), 3, hp, wp), dtype=torch.float32, device=self.device)
-        st = _stream()
-        for j, img in enumerate(imgs):
-            for f, fl in enumerate(flips):
-                L.call("shf_preprocess_level", _ptr(img), h, w, _ptr(data[j * len(flips) + f]), oh, ow, hp, wp, float(s),
-                       int(fl), self._means, st)
-                self.net.launches += 1
+        data = torch.empty((n * len(flips), 3, hp, wp), dtype=torch.float32, device=self.device)
+        L.call("shf_preprocess_level_batched", _ptr(stacked), n, h, w, _ptr(data), oh, ow, hp, wp, float(s), len(flips),
+               self._means, _stream())
+        self.net.launches += 1
         return data, (oh, ow, s)
 
     def detect_device(self, dev_images: List[torch.Tensor]):
@@ -163,6 +161,8 @@ class Detector:
         groups = {hw: [slot_of[i] for i in idxs] for hw, idxs in groups.items()}
         for (h, w), idxs in groups.items():
             scales = pyramid_scales((h, w, 3), cfg)
+            # same-sized images of the call as one (n, h, w, 3) tensor (slots of a group are consecutive)
+            stacked = dev_images[idxs[0]].unsqueeze(0) if len(idxs) == 1 else torch.stack([dev_images[i] for i in idxs])
             for li, s in enumerate(scales):
                 _, _, hp, wp = level_geometry(h, w, s, cfg.max_resolution)
                 # activations of the widest layer: 64 ch x 4 B per pixel, a few tensors live at once
@@ -170,7 +170,7 @@ class Detector:
                 chunk = max(1, min(len(idxs), 32 // nf, int(self.max_batch_bytes // max(1, per_image))))
                 for c0 in range(0, len(idxs), chunk):
                     sub = idxs[c0:c0 + chunk]
-                    data, info = self._level_batch([dev_images[i] for i in sub], s, flips)
+                    data, info = self._level_batch(stacked[c0:c0 + chunk], s, flips)
                     self.net.forward_body(data, fast=self.net.use_fast(s))
                     self.net.run_tail_batched(nf, info, b["dets"], b["offs"], image_base=sub[0], passes_total=passes,
                                               pass_base=li * nf, det_cap=b["cap"], det_thresh=cfg.thresh)

@@ -517,7 +517,7 @@ class GpuNet:
         L.call("shf_head_decode", fp, plane_stride, A, _ptr(t["wc"]), _ptr(t["bc"]), _ptr(t["wb"]), _ptr(t["bb"]), ap, H, W, Cf,
                t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])), _ptr(buf["prob"]), _ptr(buf["delta"]),
                _ptr(buf["boxes"]), _ptr(buf["keys"]), count_ptr, best_ptr, st)
-        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), n, _ptr(buf["ws"]), buf["ws_bytes"], st)
+        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), n, 32, _ptr(buf["ws"]), buf["ws_bytes"], st)
         L.call("shf_proposal_gather", _ptr(buf["skeys"]), count_ptr, best_ptr, _ptr(buf["prob"]), _ptr(buf["boxes"]), A,
                hw, buf["topn"], _ptr(buf["out_boxes"]), _ptr(buf["out_probs"]), rows_ptr,
                _ptr(dets), _ptr(pass_offsets), int(pass_idx), int(det_cap), int(bool(flip)), float(F32(im_w)),
@@ -567,7 +567,7 @@ class GpuNet:
                _ptr(t["bb"]), ap, H, W, Cf, t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])),
                _ptr(buf["prob"]), _ptr(buf["delta"]), _ptr(buf["boxes"]), _ptr(buf["keys"]), _ptr(buf["count"]),
                _ptr(buf["best"]), st)
-        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), N * n, _ptr(buf["ws"]), buf["ws_bytes"], st)
+        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), N * n, 27, _ptr(buf["ws"]), buf["ws_bytes"], st)
         L.call("shf_gather_dets_batched", _ptr(buf["skeys"]), _ptr(buf["count"]), _ptr(buf["best"]), _ptr(buf["prob"]),
                _ptr(buf["boxes"]), A, hw, min(topn, n), N // nf, nf, _ptr(dets), _ptr(pass_offsets), int(image_base),
                int(passes_total), int(pass_base), int(det_cap), float(F32(im_w)), float(F32(im_scale)),

@@ -39,6 +39,8 @@ SIGNATURES = {
     "shf_nchw_to_h2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_preprocess_level": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
                                      C.POINTER(c_double), c_void_p]),
+    "shf_preprocess_level_batched": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double,
+                                             c_int, C.POINTER(c_double), c_void_p]),
     "shf_head_decode": (c_int, [C.POINTER(c_void_p), c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 C.POINTER(c_float), c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -49,7 +51,7 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                         c_void_p]),
     "shf_sort_keys_workspace": (c_ll, [c_int]),
-    "shf_sort_keys": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
+    "shf_sort_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "shf_proposal_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                     c_float, c_void_p]),

@@ -392,7 +392,10 @@ def _run_tail(feat_nchw, wc, bc, wb, bb, im_info, topn=10000, score_thresh=0.002
     L.call("shf_head_decode", fp, 0, A, _ptr(dev(wc)), _ptr(dev(bc)), _ptr(dev(wb)), _ptr(dev(bb)),
            anchors.ctypes.data_as(C.POINTER(C.c_float)), H, W, Cc, 8, float(im_info[0]), float(im_info[1]), 0.0,
            float(F32(score_thresh)), _ptr(prob), _ptr(delta), _ptr(boxes), _ptr(keys), cptr, bptr, _stream())
-    L.call("shf_sort_keys", _ptr(keys), _ptr(skeys), n, _ptr(ws), ws_bytes, _stream())
+    L.call("shf_sort_keys", _ptr(keys), _ptr(skeys), n, 32, _ptr(ws), ws_bytes, _stream())     # stable: ties keep row order
+    full = torch.empty_like(skeys)
+    L.call("shf_sort_keys", _ptr(keys), _ptr(full), n, 0, _ptr(ws), ws_bytes, _stream())
+    assert torch.equal(full, skeys), "score-bits-only stable sort must equal the full 64-bit sort"
     L.call("shf_proposal_gather", _ptr(skeys), cptr, bptr, _ptr(prob), _ptr(boxes), A, H * W, min(topn, n), _ptr(ob),
            _ptr(op), rptr, C.c_void_p(0), C.c_void_p(0), 0, 0, 0, 0.0, 1.0, 0.05, _stream())
     R = int(meta.view(torch.int32)[1].item())
