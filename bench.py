@@ -293,8 +293,8 @@ def run_ours(args):
     def step_resident():
         b = det.detect_device(dev_imgs)
         if world > 1:
-            det.wait_results(b)
-            gather_detections(b["out_dets"], b["out_count"], world)      # the one collective: all-gather of boxes
+            # the one collective: all-gather of boxes, queued behind the box voting on its side stream
+            det.run_after_results(b, lambda: gather_detections(b["out_dets"], b["out_count"], world))
         return b
 
     def step_e2e():

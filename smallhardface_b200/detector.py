@@ -193,6 +193,16 @@ class Detector:
         self.net.launches += 3 + B
         return b
 
+    def run_after_results(self, b, fn):
+        """Runs ``fn()`` on the post-processing stream, ordered after the vote / NMS of ``b`` (e.g. the all-gather of the
+        boxes in a multi-GPU run, so that it too overlaps the next batch); ``wait_results`` then also covers it."""
+        with torch.cuda.stream(self._post_stream):
+            out = fn()
+            done = torch.cuda.Event()
+            done.record()
+        b["done"] = done
+        return out
+
     def wait_results(self, b):
         """Orders the current stream after the post-processing of ``b`` (call before reading out_dets / out_idx /
         out_count on the device; ``download`` does it itself)."""
