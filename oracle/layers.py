@@ -233,6 +233,29 @@ def softmax(x, axis=1):
     return (e / e.sum(axis=axis, keepdims=True, dtype=F32)).astype(F32)
 
 
+def batch_norm(x, mean, var, factor, eps=1e-5):
+    """BatchNormLayer forward with use_global_stats (TEST), ``batch_norm_layer.cpp:98-104,112-117,147-165``:
+    scale_factor = 0 if blobs[2][0] == 0 else 1 / blobs[2][0]; mean_ = blobs[0]*scale_factor; variance_ = blobs[1]*scale_factor;
+    top = (x - mean_) / sqrt(variance_ + eps), all in float32."""
+    x = np.asarray(x, dtype=F32)
+    f = F32(np.asarray(factor, dtype=F32).reshape(-1)[0])
+    sf = F32(0) if f == 0 else F32(1) / f
+    m = np.asarray(mean, F32) * sf
+    v = np.sqrt(np.asarray(var, F32) * sf + F32(eps))
+    shp = (1, -1) + (1,) * (x.ndim - 2)
+    return ((x - m.reshape(shp)) / v.reshape(shp)).astype(F32, copy=False)
+
+
+def scale(x, gamma, beta=None):
+    """ScaleLayer forward, per-channel form (axis 1, num_axes 1; ``scale_layer.cpp:117-147``): top = x * gamma[c] (+ beta[c])."""
+    x = np.asarray(x, dtype=F32)
+    shp = (1, -1) + (1,) * (x.ndim - 2)
+    y = x * np.asarray(gamma, F32).reshape(shp)
+    if beta is not None:
+        y = y + np.asarray(beta, F32).reshape(shp)
+    return y.astype(F32, copy=False)
+
+
 def bilinear_filler(shape):
     """``filler.hpp:244-262`` BilinearFiller: f = ceil(k/2), c = (2f-1-f%2)/(2f),
     w[x,y] = (1-|x/f-c|)(1-|y/f-c|), identical for every (n,c) plane."""

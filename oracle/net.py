@@ -65,6 +65,15 @@ class OracleNet:
                     y = L.deconv(xs[0], w, bias, (p["ph"], p["pw"]), (p["sh"], p["sw"]), (p["dh"], p["dw"]), p["group"])
             elif t == "ReLU":
                 y = L.relu(xs[0], p["negative_slope"])
+            elif t == "BatchNorm":
+                if not p["use_global_stats"]:
+                    raise ValueError("BatchNorm %s: batch statistics are a TRAIN-phase mode" % spec_l.name)
+                mean, var, factor = (self.params[k] for k in spec_l.param_keys)
+                y = L.batch_norm(xs[0], mean, var, factor, p["eps"])
+            elif t == "Scale":
+                gamma = self.params[spec_l.param_keys[0]]
+                beta = self.params[spec_l.param_keys[1]] if p["bias_term"] else None
+                y = L.scale(xs[0], gamma, beta)
             elif t == "Pooling":
                 if p["pool"] != 0:
                     raise ValueError("only MAX pooling is on the hot path")

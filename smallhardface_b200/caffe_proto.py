@@ -84,7 +84,16 @@ SCHEMA: Dict[str, Dict[str, Tuple[int, str, str]]] = {
         "softmax_param": (125, "SoftmaxParameter", "o"),
         "python_param": (130, "PythonParameter", "o"),
         "reshape_param": (133, "ReshapeParameter", "o"),
+        "batch_norm_param": (139, "BatchNormParameter", "o"),
+        "scale_param": (142, "ScaleParameter", "o"),
         "input_param": (143, "InputParameter", "o"),
+    },
+    "BatchNormParameter": {                                              # caffe.proto:507-527
+        "use_global_stats": (1, "bool", "o"), "moving_average_fraction": (2, "float", "o"), "eps": (3, "float", "o"),
+    },
+    "ScaleParameter": {                                                  # caffe.proto:1099-1129
+        "axis": (1, "int32", "o"), "num_axes": (2, "int32", "o"), "filler": (3, "FillerParameter", "o"),
+        "bias_term": (4, "bool", "o"), "bias_filler": (5, "FillerParameter", "o"),
     },
     "ConcatParameter": {"concat_dim": (1, "uint32", "o"), "axis": (2, "int32", "o")},  # :496-505
     "ConvolutionParameter": {                                            # caffe.proto:573-624
@@ -146,6 +155,8 @@ DEFAULTS: Dict[Tuple[str, str], Any] = {
     ("SoftmaxParameter", "axis"): 1, ("SoftmaxParameter", "engine"): 0,
     ("ReLUParameter", "negative_slope"): 0.0, ("ReLUParameter", "engine"): 0,
     ("ReshapeParameter", "axis"): 0, ("ReshapeParameter", "num_axes"): -1,
+    ("BatchNormParameter", "moving_average_fraction"): 0.999, ("BatchNormParameter", "eps"): 1e-5,
+    ("ScaleParameter", "axis"): 1, ("ScaleParameter", "num_axes"): 1, ("ScaleParameter", "bias_term"): False,
     ("PythonParameter", "param_str"): "", ("PythonParameter", "share_in_parallel"): False,
     ("FillerParameter", "type"): "constant", ("FillerParameter", "value"): 0.0,
     ("FillerParameter", "min"): 0.0, ("FillerParameter", "max"): 1.0,

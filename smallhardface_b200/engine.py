@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from . import lib as L
-from .graph import NetSpec, LayerSpec, parse_python_param_str
+from .graph import NetSpec, LayerSpec, fold_batchnorm_scale, parse_python_param_str
 
 F32 = np.float32
 
@@ -248,16 +248,35 @@ class GpuNet:
                 continue
             if l.type == "Convolution":
                 p = l.p
-                relu = False
-                if i + 1 < len(layers) and layers[i + 1].type == "ReLU" and layers[i + 1].bottoms == l.tops \
-                        and layers[i + 1].tops == l.tops and layers[i + 1].p["negative_slope"] == 0.0:
-                    relu = True
                 w = params[l.param_keys[0]]
                 b = params[l.param_keys[1]] if p["bias_term"] else None
+                # TEST-phase BatchNorm / Scale followers are per-channel affine maps: fold them into the weights and
+                # the bias, so "conv + BN + Scale + ReLU" is still one launch with the bias+ReLU epilogue
+                chain, j, top = [], i + 1, l.tops[0]
+                while j < len(layers) and layers[j].type in ("BatchNorm", "Scale") and layers[j].bottoms == [top]:
+                    f = layers[j]
+                    if f.tops != f.bottoms and len(consumers.get(top, [])) != 1:
+                        break                                    # the un-normalised blob has another reader
+                    if f.type == "BatchNorm":
+                        if not f.p["use_global_stats"]:
+                            raise L.ShfError("BatchNorm %s: batch statistics (use_global_stats: false) are a TRAIN-phase mode" % f.name)
+                        chain.append(("BatchNorm", params[f.param_keys[0]], params[f.param_keys[1]], params[f.param_keys[2]], f.p["eps"]))
+                    else:
+                        chain.append(("Scale", params[f.param_keys[0]], params[f.param_keys[1]] if f.p["bias_term"] else None))
+                    if f.tops != f.bottoms:
+                        self.fused_blobs.add(top)
+                    top = f.tops[0]
+                    j += 1
+                if chain:
+                    w, b = fold_batchnorm_scale(w, b, chain)
+                relu = False
+                if j < len(layers) and layers[j].type == "ReLU" and layers[j].bottoms == [top] \
+                        and layers[j].tops == [top] and layers[j].p["negative_slope"] == 0.0:
+                    relu = True
                 if (p["sh"], p["sw"]) != (1, 1) or p["group"] != 1 or p["kh"] != p["kw"] or p["dh"] != p["dw"] or p["ph"] != p["pw"]:
                     raise L.ShfError("conv %s: only stride-1, ungrouped, square kernels are on the hot path" % l.name)
                 cin = w.shape[1]
-                st = dict(relu=relu, k=p["kh"], dil=p["dh"], cout=p["num_output"], cin=cin,
+                st = dict(relu=relu, k=p["kh"], dil=p["dh"], cout=p["num_output"], cin=cin, top=top,
                           bias=None if b is None else torch.from_numpy(np.ascontiguousarray(b, F32)).to(dev))
                 if cin == 3:
                     if not (p["kh"] == 3 and p["ph"] == 1 and p["dh"] == 1 and p["num_output"] == 64):
@@ -279,18 +298,20 @@ class GpuNet:
                         packed8, k8 = pack_conv_weights_hf8(w)
                         assert k8 == k
                         st["w8"] = torch.from_numpy(packed8).to(dev)
-                    nxt = i + (2 if relu else 1)
+                    nxt = j + (1 if relu else 0)
                     pl = layers[nxt] if nxt < len(layers) else None
-                    if (self.fuse_pool and pl is not None and pl.type == "Pooling" and pl.bottoms == l.tops
+                    if (self.fuse_pool and pl is not None and pl.type == "Pooling" and pl.bottoms == [top]
                             and (pl.p["pool"], pl.p["kh"], pl.p["kw"], pl.p["sh"], pl.p["sw"], pl.p["ph"], pl.p["pw"]) == (0, 2, 2, 2, 2, 0, 0)):
                         st["pool_top"] = pl.tops[0]
-                        st["write_full"] = len(consumers.get(l.tops[0], [])) > 1      # e.g. conv4_3 also feeds conv4_256
+                        st["write_full"] = len(consumers.get(top, [])) > 1      # e.g. conv4_3 also feeds conv4_256
                         self.ops.append(("conv", l, st))
                         i = nxt + 1
                         continue
                     self.ops.append(("conv", l, st))
-                i += 2 if relu else 1
+                i = j + (1 if relu else 0)
                 continue
+            if l.type in ("BatchNorm", "Scale"):
+                raise L.ShfError("%s %s does not follow a convolution it can be folded into (unsupported pattern)" % (l.type, l.name))
             if l.type == "ReLU":
                 raise L.ShfError("ReLU %s is not fused into a preceding convolution (unsupported pattern)" % l.name)
             if l.type == "Pooling":
@@ -427,7 +448,7 @@ class GpuNet:
             x = T[l.bottoms[0]]
             if kind == "conv1":
                 n, _, h, w = x.shape
-                out = self._alloc_out(l.tops[0], n, h, w, s["cout"], fmt)
+                out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
                 L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
                        s["scale"], int(s["relu"]), out.fmt, st)
             elif kind == "conv":
@@ -437,7 +458,7 @@ class GpuNet:
                 out = None
                 wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
                 if not fused or s["write_full"]:
-                    out = self._alloc_out(l.tops[0], x.n, x.h, x.w, s["cout"], fmt)
+                    out = self._alloc_out(s["top"], x.n, x.h, x.w, s["cout"], fmt)
                 if self.profile:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e0.record()

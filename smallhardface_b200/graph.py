@@ -22,7 +22,7 @@ from . import caffe_proto as cp
 TRAIN, TEST = 0, 1
 
 SUPPORTED = ("Input", "Convolution", "Deconvolution", "ReLU", "Pooling", "Concat", "Reshape",
-             "Softmax", "Python", "Split")
+             "Softmax", "Python", "Split", "BatchNorm", "Scale")
 
 
 @dataclass
@@ -161,6 +161,15 @@ class NetSpec:
                 spec.p = dict(dims=[int(d) for d in r.shape.dim], axis=int(r.axis), num_axes=int(r.num_axes))
             elif l.type == "Softmax":
                 spec.p = dict(axis=int(l.softmax_param.axis))
+            elif l.type == "BatchNorm":                    # batch_norm_layer.cpp:12-21
+                q = l.batch_norm_param
+                spec.p = dict(use_global_stats=bool(q.use_global_stats) if q.has("use_global_stats") else phase == TEST,
+                              eps=float(q.eps))
+            elif l.type == "Scale":                        # scale_layer.cpp:12-60 (per-channel form only)
+                q = l.scale_param
+                if len(spec.bottoms) != 1 or int(q.axis) != 1 or int(q.num_axes) != 1:
+                    raise ValueError("%s: only the per-channel Scale (one bottom, axis 1, num_axes 1) is supported" % l.name)
+                spec.p = dict(bias_term=bool(q.bias_term))
             elif l.type == "Python":
                 q = l.python_param
                 spec.p = dict(module=q.module, layer=q.layer, param_str=q.param_str)
@@ -171,9 +180,9 @@ class NetSpec:
     # -- parameters ------------------------------------------------------------------
     def _assign_params(self) -> None:
         for spec in self.layers:
-            if spec.type not in ("Convolution", "Deconvolution"):
+            if spec.type not in ("Convolution", "Deconvolution", "BatchNorm", "Scale"):
                 continue
-            n = 2 if spec.p["bias_term"] else 1
+            n = 3 if spec.type == "BatchNorm" else (2 if spec.p["bias_term"] else 1)
             pspecs = spec.msg.param
             for i in range(n):
                 pname = pspecs[i].name if i < len(pspecs) and pspecs[i].has("name") else ""
@@ -187,6 +196,15 @@ class NetSpec:
 
     def check_param_shape(self, spec: LayerSpec, cin: int) -> List[Tuple[int, ...]]:
         p = spec.p
+        if spec.type in ("BatchNorm", "Scale"):
+            # batch_norm_layer.cpp:25-36: mean (C), variance (C), moving-average factor (1); scale_layer.cpp: gamma (C)[, beta (C)]
+            shapes = [(cin,), (cin,), (1,)] if spec.type == "BatchNorm" else [(cin,)] * (2 if p["bias_term"] else 1)
+            for key, shp in zip(spec.param_keys, shapes):
+                prev = self.param_shapes.get(key)
+                if prev is not None and prev != shp:
+                    raise ValueError("Cannot share param %s: shape mismatch %s vs %s" % (key, prev, shp))
+                self.param_shapes[key] = shp
+            return shapes
         g = p["group"]
         if spec.type == "Convolution":
             if cin % g or p["num_output"] % g:
@@ -240,6 +258,9 @@ class NetSpec:
                 out = (n, c, ho, wo)
             elif t in ("ReLU", "Softmax"):
                 out = bs[0]
+            elif t in ("BatchNorm", "Scale"):
+                self.check_param_shape(spec, bs[0][1] if len(bs[0]) > 1 else 1)
+                out = bs[0]
             elif t == "Split":
                 for nm in spec.tops:
                     shapes[nm] = bs[0]
@@ -264,6 +285,34 @@ class NetSpec:
                 raise AssertionError(t)
             shapes[spec.tops[0]] = out
         return shapes
+
+
+def fold_batchnorm_scale(w, b, chain):
+    """Folds a Convolution's TEST-phase BatchNorm / Scale followers into its weights and bias.
+    ``chain``: list of ("BatchNorm", mean, var, factor, eps) / ("Scale", gamma, beta-or-None) in layer order.
+    BatchNorm with global stats (batch_norm_layer.cpp:98-104,147-165): s = 0 if factor == 0 else 1 / factor;
+    y = (x - mean*s) / sqrt(var*s + eps).  Scale (scale_layer.cpp): y = x * gamma + beta.  Everything is affine per
+    output channel, so conv -> BN -> Scale == conv with w' = w * a, b' = b * a + c (float64 arithmetic, rounded once)."""
+    w = np.asarray(w, dtype=np.float64)
+    co = w.shape[0]
+    a = np.ones(co, dtype=np.float64)
+    c = np.zeros(co, dtype=np.float64) if b is None else np.asarray(b, dtype=np.float64).copy()
+    for item in chain:
+        if item[0] == "BatchNorm":
+            _, mean, var, factor, eps = item
+            f = float(np.asarray(factor).reshape(-1)[0])
+            s = 0.0 if f == 0 else 1.0 / f
+            inv = 1.0 / np.sqrt(np.asarray(var, np.float64) * s + eps)
+            a = a * inv
+            c = (c - np.asarray(mean, np.float64) * s) * inv
+        elif item[0] == "Scale":
+            _, gamma, beta = item
+            g = np.asarray(gamma, np.float64)
+            a = a * g
+            c = c * g + (0.0 if beta is None else np.asarray(beta, np.float64))
+        else:                                                       # pragma: no cover
+            raise AssertionError(item[0])
+    return (w * a[:, None, None, None]).astype(np.float32), c.astype(np.float32)
 
 
 def reshape_shape(bottom, dims, axis, num_axes, lname="reshape"):

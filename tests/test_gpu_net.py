@@ -224,3 +224,25 @@ def test_detector_mixed_sizes_batch_equals_individual(nets):
         alone = det.detect([im])[0]
         assert res.shape == alone.shape and np.array_equal(res, alone)
     assert len({r.shape[0] for r in together}) > 1
+
+
+def test_batchnorm_scale_relu_folded_into_the_conv_launch():
+    """Convolution -> BatchNorm -> Scale -> ReLU (the epilogue BASELINE's north_star names; no shipped template has
+    one) runs as ONE launch per conv with the affine maps folded into weights and bias, and equals the
+    layer-by-layer oracle (batch_norm_layer.cpp / scale_layer.cpp semantics)."""
+    from test_host_logic import BN_NET, bn_net_params
+    net = cp.parse_text(BN_NET, "NetParameter")
+    onet = OracleNet(net, None, engine="torch", fast=True)
+    params = bn_net_params(onet.spec)
+    onet.params.update(params)
+    gnet = GpuNet(NetSpec(net), params, "cuda:0", fast_min_scale=None)
+    assert [k for k, l, s in gnet.ops] == ["conv1", "conv"]              # two launches for eight layers
+    x = (np.random.RandomState(1).rand(1, 3, 24, 40) * 255 - 110).astype(F32)
+    ref = onet.forward(data=x)
+    assert gnet.forward(torch.from_numpy(x).to(DEV), (24, 40, 1.0)) is None      # no detection tail in this net
+    for nm, want in (("c1", onet.blobs["c1"]), ("c2_out", ref["c2_out"])):
+        got = gnet.blob_nchw(nm).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), nm
+    with pytest.raises(Exception):
+        gnet.blob_nchw("c2_bn")                                             # folded away, never materialised
+

@@ -124,6 +124,65 @@ def test_conv1_tensor_core_weight_packing():
     assert np.abs(rec - w.reshape(64, 27)).max() <= np.abs(w).max() * 2.0 ** -21
 
 
+BN_NET = """
+name: "bn_test"
+input: "data"
+input_shape { dim: 1 dim: 3 dim: 24 dim: 40 }
+layer { name: "c1" type: "Convolution" bottom: "data" top: "c1" convolution_param { num_output: 64 kernel_size: 3 pad: 1 bias_term: false } }
+layer { name: "c1_bn" type: "BatchNorm" bottom: "c1" top: "c1" batch_norm_param { use_global_stats: true } }
+layer { name: "c1_scale" type: "Scale" bottom: "c1" top: "c1" scale_param { bias_term: true } }
+layer { name: "c1_relu" type: "ReLU" bottom: "c1" top: "c1" }
+layer { name: "c2" type: "Convolution" bottom: "c1" top: "c2" convolution_param { num_output: 64 kernel_size: 3 pad: 1 } }
+layer { name: "c2_bn" type: "BatchNorm" bottom: "c2" top: "c2_bn" batch_norm_param { eps: 0.001 } }
+layer { name: "c2_scale" type: "Scale" bottom: "c2_bn" top: "c2_out" }
+layer { name: "c2_relu" type: "ReLU" bottom: "c2_out" top: "c2_out" }
+"""
+
+
+def bn_net_params(spec, seed=0):
+    """Random but well-conditioned parameters for BN_NET, keyed like graph.load_weights."""
+    rng = np.random.RandomState(seed)
+    spec.infer_shapes({})
+    params = {}
+    for l in spec.layers:
+        for i, key in enumerate(l.param_keys):
+            shp = spec.param_shapes[key]
+            if l.type == "Convolution":
+                fan = shp[1] * shp[2] * shp[3] if len(shp) == 4 else 1
+                params[key] = (rng.randn(*shp) * (np.sqrt(2.0 / fan) if len(shp) == 4 else 0.1)).astype(np.float32)
+            elif l.type == "BatchNorm":
+                params[key] = [rng.randn(*shp) * 3, rng.rand(*shp) * 4 + 0.5, np.full(shp, 1.7)][i].astype(np.float32)
+            else:
+                params[key] = ([rng.rand(*shp) + 0.5, rng.randn(*shp) * 0.2][i]).astype(np.float32)
+    return params
+
+
+def test_batchnorm_scale_fold_equals_layerwise_oracle():
+    """conv -> BatchNorm -> Scale (-> ReLU) as ONE convolution with folded weights equals the layer-by-layer oracle."""
+    from oracle import layers as OL
+    from oracle.net import OracleNet
+    from smallhardface_b200 import caffe_proto as cp
+    from smallhardface_b200.graph import NetSpec, fold_batchnorm_scale
+    net = cp.parse_text(BN_NET, "NetParameter")
+    onet = OracleNet(net, None, engine="torch", fast=True)
+    params = bn_net_params(onet.spec)
+    onet.params.update(params)
+    x = (np.random.RandomState(1).rand(1, 3, 24, 40) * 255 - 110).astype(np.float32)
+    out = onet.forward(data=x)
+    assert list(out) == ["c2_out"]
+    by = {l.name: l for l in onet.spec.layers}
+    k = lambda n, i: params[by[n].param_keys[i]]
+    assert by["c2_bn"].p == dict(use_global_stats=True, eps=np.float32(0.001)) or abs(by["c2_bn"].p["eps"] - 0.001) < 1e-9
+    w1, b1 = fold_batchnorm_scale(k("c1", 0), None, [("BatchNorm", k("c1_bn", 0), k("c1_bn", 1), k("c1_bn", 2), 1e-5),
+                                                     ("Scale", k("c1_scale", 0), k("c1_scale", 1))])
+    y1 = OL.relu(OL.conv(x, w1, b1, pad=(1, 1), engine="torch"))
+    assert np.abs(y1 - onet.blobs["c1"]).max() <= 2e-5 * np.abs(y1).max()
+    w2, b2 = fold_batchnorm_scale(k("c2", 0), k("c2", 1), [("BatchNorm", k("c2_bn", 0), k("c2_bn", 1), k("c2_bn", 2), by["c2_bn"].p["eps"]),
+                                                           ("Scale", k("c2_scale", 0), None)])
+    y2 = OL.relu(OL.conv(onet.blobs["c1"], w2, b2, pad=(1, 1), engine="torch"))
+    assert np.abs(y2 - out["c2_out"]).max() <= 2e-5 * np.abs(y2).max()
+
+
 # ---- caffe / caffe_pb2 shims ---------------------------------------------------------------------
 def test_caffe_pb2_shim_text_and_wire():
     from smallhardface_b200 import compat

@@ -131,3 +131,21 @@ def test_relu():
     x = np.array([-2.0, 0.0, 3.0], F32)
     assert L.relu(x).tolist() == [0, 0, 3]
     assert np.allclose(L.relu(x, 0.1), [-0.2, 0, 3])
+
+
+def test_batchnorm_global_stats_and_scale():
+    """batch_norm_layer.cpp:98-104,147-165 with use_global_stats: the stored sums are divided by the moving-average
+    factor (0 -> 0), then y = (x - mean) / sqrt(var + eps); scale_layer.cpp: y = x * gamma + beta per channel."""
+    rng = np.random.RandomState(0)
+    x = rng.randn(2, 3, 4, 5).astype(np.float32)
+    mean_sum = np.array([1.0, -2.0, 0.5], np.float32) * 4
+    var_sum = np.array([4.0, 0.25, 1.0], np.float32) * 4
+    y = L.batch_norm(x, mean_sum, var_sum, np.array([4.0], np.float32), eps=1e-5)
+    for c, (m, v) in enumerate([(1.0, 4.0), (-2.0, 0.25), (0.5, 1.0)]):
+        assert np.allclose(y[:, c], (x[:, c] - m) / np.sqrt(v + 1e-5), rtol=1e-6, atol=1e-6)
+    y0 = L.batch_norm(x, mean_sum, var_sum, np.array([0.0], np.float32), eps=1e-5)      # factor 0: mean = var = 0
+    assert np.allclose(y0, x / np.sqrt(np.float32(1e-5)), rtol=1e-6)
+    g, b = np.array([2.0, -1.0, 0.5], np.float32), np.array([0.1, 0.2, -0.3], np.float32)
+    z = L.scale(x, g, b)
+    assert np.allclose(z[:, 1], -x[:, 1] + 0.2) and np.allclose(L.scale(x, g)[:, 2], 0.5 * x[:, 2])
+
