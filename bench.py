@@ -391,14 +391,14 @@ def run_ours(args):
                 line["e2e_plugin"] = {"error": repr(e)[:200]}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ips, desc, dt = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2))
+            ips, desc, dt = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2, 3))
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
                                     "algorithm": "the reference's: im2col + OpenBLAS sgemm per conv, separate ReLU / pool passes, "
                                                  "NumPy ProposalLayer and bbox_vote (SURVEY 8d proxy i)"}
             # SURVEY 8d proxy (ii): best-effort CPU (oneDNN direct convolutions through torch), same sample
             import torch as _t
             _t.set_num_threads(cores)
-            ips2, desc2, _ = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2), engine="torch")
+            ips2, desc2, _ = cpu_baseline_sample(proto, model, imgs[0], levels=(0, 1, 2, 3), engine="torch")
             line["cpu_baseline_onednn"] = {"value": ips2, "unit": "images/s", "cores": cores, "kind": "port",
                                            "sample": desc2, "algorithm": "same layers with torch/oneDNN fp32 convolutions"}
         print(json.dumps(line))

@@ -494,6 +494,27 @@ def test_nms_host_abi_symbol(golden_dir):
     assert order[keep[:num.value]].tolist() == OP.nms(d, 0.4, OP.NMS_GPU)
 
 
+def test_preprocess_level_batched_equals_per_image_kernel():
+    """One launch for a stacked (N, h, w, 3) batch x {plain, mirrored} gives, slot for slot, the single-image kernel's bits."""
+    from smallhardface_b200.detector import level_geometry
+    rng = np.random.RandomState(8)
+    n, h, w, scale = 3, 70, 101, 1.3671875
+    ims = rng.randint(0, 256, (n, h, w, 3)).astype(np.uint8)
+    oh, ow, hp, wp = level_geometry(h, w, scale)
+    means = (C.c_double * 3)(*OPRE.PIXEL_MEANS.ravel())
+    stacked = dev(ims)
+    for passes in (1, 2):
+        out = torch.empty((n * passes, 3, hp, wp), dtype=torch.float32, device=DEV)
+        L.call("shf_preprocess_level_batched", _ptr(stacked), n, h, w, _ptr(out), oh, ow, hp, wp, float(scale), passes,
+               means, _stream())
+        for j in range(n):
+            for f in range(passes):
+                one = torch.empty((1, 3, hp, wp), dtype=torch.float32, device=DEV)
+                L.call("shf_preprocess_level", _ptr(stacked[j]), h, w, _ptr(one), oh, ow, hp, wp, float(scale), f, means,
+                       _stream())
+                assert torch.equal(out[j * passes + f], one[0]), (passes, j, f)
+
+
 def test_bbox_vote_vs_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "bbox_vote.npz"))
     tags = ["n0", "n1", "n2far", "n400", "n3000"]
