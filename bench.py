@@ -280,7 +280,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     proto, model = deploy.write_synthetic_deployment(deploy_dir(), dilation=True)
-    det = Detector(proto, model, dev, DetectConfig())
+    cfg = DetectConfig()
+    if args.fast_min_scale is not None:
+        cfg.fast_min_scale = None if args.fast_min_scale.lower() == "none" else float(args.fast_min_scale)
+    det = Detector(proto, model, dev, cfg)
     imgs = make_images(rank)
     dev_imgs = det.upload(imgs)
     torch.cuda.synchronize()
@@ -414,6 +417,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--fast-min-scale", default=None,
+                    help="operand-format policy override for trade-off tables: a number, or 'none' for split fp16 on every "
+                         "level (default: DetectConfig's 1.3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
