@@ -77,8 +77,10 @@ if out:
     with open(os.path.join(prof, "%s_ncu_full.md" % tag), "w") as f:
         f.write("# %s -- `ncu --set full --clock-control none --import-source on` captures (one launch each)\n\n" % tag)
         f.write("Commands: `ncu --set full --clock-control none --import-source on -k regex:conv_stream -s 2 -c 1 -o gpurun_out/<name> "
-                "python tools/ncu_one.py 8 512 512 256 256 3 1 <fmt>` (the conv4_2-class shape of the 2048-px level: 512->512 3x3 at "
-                "256x256; fmt 0 = split fp16, 1 = fp16 + fp8) and the same for `conv1_tc` (3->64 at 2048x2048).\n\n")
+                "python tools/ncu_one.py 8 <Cin> <Cout> <H> <W> 3 1 <fmt>` on shapes of the 2048-px level (conv4_2: 512->512 at 256x256; "
+                "conv2_2: 128->128 at 1024x1024; conv1_2: 64->64 at 2048x2048; fmt 0 = split fp16, 1 = fp16 + fp8) and the same for "
+                "`conv1_tc` (3->64 at 2048x2048).  Read: tensor pipe 94 % / 91 % active on conv4_2 (h2 / hf8), 86 % on conv2_2 hf8, "
+                "64 % on the 64-channel conv1_2 (shared-memory operand reads: l1tex 80 %); DRAM traffic = algorithmic bytes.\n\n")
         f.write("| capture | " + " | ".join(k.replace("_", "\\_") for k in KEYS) + " |\n|---|" + "---:|" * len(KEYS) + "\n")
         for rep, d in out:
             f.write("| %s | " % rep + " | ".join("%s %s" % (d.get(k, ("", ""))[0], d.get(k, ("", ""))[1]) for k in KEYS) + " |\n")
