@@ -35,6 +35,18 @@ void shf_set_error(const char* fmt, ...);
 
 #define SHF_LAUNCH_CHECK() SHF_CUDA_CHECK(cudaGetLastError())
 
+// Tuning / timing probes (SHF_PROBE_* environment variables; some give WRONG results by design) are honoured only by a
+// library built with -DSHF_PROBES (`make clean && make PROBES=1`): a stray variable cannot perturb a product build.
+#include <stdlib.h>
+inline const char* shf_probe_env(const char* name) {
+#ifdef SHF_PROBES
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------
 // Activation formats.  Both are NHWC, 4 bytes per element in two equally sized planes, C a multiple of 8:
 //

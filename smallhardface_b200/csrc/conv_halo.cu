@@ -337,7 +337,7 @@ extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* 
   p.xw = (ksize == 1) ? kTW : (narrow ? kTW + 2 * p.pad : 16);
   p.xh = kTH + 2 * p.pad;
   p.bo_mode = (g_conv_impl == 2 || g_conv_impl == 4) ? 1 : 0;
-  p.no_shift = getenv("SHF_PROBE_NOSHIFT") ? 1 : 0;  // timing probe (wrong results): isolates the cost of unaligned groups
+  p.no_shift = shf_probe_env("SHF_PROBE_NOSHIFT") ? 1 : 0;  // timing probe (wrong results): isolates the cost of unaligned groups
   p.a_tx = 2 * p.xh * p.xw * 128;
   p.a_bytes = (p.a_tx + 1023) & ~1023;               // keep every stage 1024-byte aligned
   p.b_bytes = 2 * bn * 128;
@@ -345,8 +345,8 @@ extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* 
   p.na = (2 * p.a_bytes + 3 * p.b_bytes <= budget && p.cin_chunks > 1) ? 2 : 1;
   p.nb = (budget - p.na * p.a_bytes) / p.b_bytes;
   if (p.nb > kMaxStages) p.nb = kMaxStages;
-  if (const char* e = getenv("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
-  if (const char* e = getenv("SHF_PROBE_NA")) { int v = atoi(e); if (v >= 1 && v <= 2 && v <= p.na) p.na = v; }
+  if (const char* e = shf_probe_env("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
+  if (const char* e = shf_probe_env("SHF_PROBE_NA")) { int v = atoi(e); if (v >= 1 && v <= 2 && v <= p.na) p.na = v; }
   if (bn == 64) {
     // 4 x 64 TMEM columns = half the SM's tensor memory: keep shared memory under half an SM as well so that two
     // CTAs are co-resident and one's epilogue overlaps the other's main loop

@@ -473,28 +473,28 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   // A-ring depth: a halo stage lasts taps x 4 k-steps of MMAs; when that is short (one 64-channel chunk per tile at
   // BN = 64: ~2-3k cycles, or 1x1 convs) two stages do not cover the ~4k cycles a 46 KB halo takes to arrive
   p.na = (p.taps == 1) ? kMaxA : ((bn == 64 || p.cin_chunks == 1) ? 3 : 2);
-  if (const char* e = getenv("SHF_PROBE_NA")) { int v = atoi(e); if (v >= 1 && v <= kMaxA) p.na = v; }
+  if (const char* e = shf_probe_env("SHF_PROBE_NA")) { int v = atoi(e); if (v >= 1 && v <= kMaxA) p.na = v; }
   while (p.na > 1 && p.na * p.a_bytes + 4 * p.b_bytes > budget) --p.na;
   p.nb = (budget - p.na * p.a_bytes) / p.b_bytes;
   if (p.nb > kMaxB) p.nb = kMaxB;
   // conv1_2-class layers (one N tile, 9 stages of weights in all): keep the weights in shared memory for the whole
   // kernel -- streaming them again for every 128-pixel tile was most of that layer's L2->SM traffic
-  p.b_resident = (cout == bn && p.taps * p.cin_chunks <= p.nb && p.na >= 2 && !getenv("SHF_PROBE_NO_RESIDENT")) ? 1 : 0;
+  p.b_resident = (cout == bn && p.taps * p.cin_chunks <= p.nb && p.na >= 2 && !shf_probe_env("SHF_PROBE_NO_RESIDENT")) ? 1 : 0;
   if (p.b_resident) p.nb = p.taps * p.cin_chunks;
-  if (const char* e = getenv("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
+  if (const char* e = shf_probe_env("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
   SHF_REQUIRE(p.nb >= 2, "shf_conv_igemm: halo tile of %d bytes leaves no room for the weight ring", p.a_bytes);
   p.tiles_x = ((W + kTW - 1) / kTW + ctas - 1) / ctas;          // tile pairs along x when ctas == 2
   p.tiles_y = (H + kTH - 1) / kTH;
   p.n_tiles = cout / bn;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * batch;
   p.chunks_per_phase = (p.taps == 9) ? 1 : 9;
-  if (const char* e = getenv("SHF_PROBE_G")) { int v = atoi(e); if (v >= 1) p.chunks_per_phase = v; }
+  if (const char* e = shf_probe_env("SHF_PROBE_G")) { int v = atoi(e); if (v >= 1) p.chunks_per_phase = v; }
   p.ctot = out_channels_total;
   p.cout_offset = out_channel_offset;
   p.relu = relu;
   p.in_fmt = in_format;
   p.probe = 0;
-  if (const char* e = getenv("SHF_PROBE_EPI")) p.probe = atoi(e);
+  if (const char* e = shf_probe_env("SHF_PROBE_EPI")) p.probe = atoi(e);
   p.out_fmt = out_format;
   p.out_scale = out_scale;
   p.bias = bias;

@@ -1,4 +1,6 @@
-"""Epilogue cost probe for the tcgen05 conv (timing only): SHF_PROBE_EPI = 0 production, 1 no global stores, 2 drain only."""
+"""Epilogue / pipeline elimination probes for the tcgen05 conv (timing only, WRONG results): needs a probe build
+(`make -C smallhardface_b200/csrc clean && make -C smallhardface_b200/csrc PROBES=1`).  SHF_PROBE_EPI bits: 1 = no global
+stores, 2 = drain only, 4 = no activation loads, 8 = no MMAs."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
