@@ -17,3 +17,14 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The CUDA extension is git-ignored (it travels with the working tree): build it in-tree if a fresh checkout is
+    being tested.  This only compiles; nothing here provides a substitute for the kernels."""
+    from smallhardface_b200 import lib
+    if not os.path.exists(lib.LIB_PATH):
+        lib.build()
+    return lib.LIB_PATH
+
