@@ -274,6 +274,16 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    from smallhardface_b200 import lib as _lib
+    if not os.path.exists(_lib.LIB_PATH):          # fresh checkout: compile the git-ignored extension in-tree (rank 0 first)
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            _lib.build()
+        else:
+            for _ in range(600):
+                if os.path.exists(_lib.LIB_PATH):
+                    break
+                time.sleep(1.0)
+            time.sleep(2.0)
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
