@@ -17,6 +17,20 @@ def test_pooling_square_kat():                  # test_pooling_layer.cpp:49-119
     assert np.array_equal(mask[0, 0], [[5, 2, 2, 9], [5, 12, 12, 9]])
 
 
+def test_pooling_rect_kernels_kat():            # test_pooling_layer.cpp:121-245 (RectHigh 3x2), :247-375 (RectWide 2x3)
+    magic6 = np.array([[35, 1, 6, 26, 19, 24], [3, 32, 7, 21, 23, 25], [31, 9, 2, 22, 27, 20],
+                       [8, 28, 33, 17, 10, 15], [30, 5, 34, 12, 14, 16], [4, 36, 29, 13, 18, 11]], F32)
+    x = np.tile(magic6, (2, 2, 1, 1))
+    y, mask = L.max_pool(x, (3, 2), (1, 1), return_mask=True)
+    assert y.shape == (2, 2, 4, 5)
+    assert np.array_equal(y[1, 0], [[35, 32, 26, 27, 27], [32, 33, 33, 27, 27], [31, 34, 34, 27, 27], [36, 36, 34, 18, 18]])
+    assert np.array_equal(mask[0, 1], [[0, 7, 3, 16, 16], [7, 20, 20, 16, 16], [12, 26, 26, 16, 16], [31, 31, 26, 34, 34]])
+    y, mask = L.max_pool(x, (2, 3), (1, 1), return_mask=True)
+    assert y.shape == (2, 2, 5, 4)
+    assert np.array_equal(y[0, 1], [[35, 32, 26, 26], [32, 32, 27, 27], [33, 33, 33, 27], [34, 34, 34, 17], [36, 36, 34, 18]])
+    assert np.array_equal(mask[1, 1], [[0, 7, 3, 3], [7, 7, 16, 16], [20, 20, 20, 16], [26, 26, 26, 21], [31, 31, 26, 34]])
+
+
 def test_pooling_padded_kat():                  # test_pooling_layer.cpp:478-521 TestForwardMaxPadded
     plane = np.array([[1, 2, 4], [2, 3, 2], [4, 2, 1]], F32)
     y = L.max_pool(plane[None, None], (3, 3), (2, 2), (2, 2))
