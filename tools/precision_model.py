@@ -54,13 +54,23 @@ def quant_act(x, scheme):
     al = x - ah
     if scheme == "h2":
         return ah + rn16(al)
-    if scheme == "h2f8" or scheme.startswith("mix"):
-        return ah + e5m2(al * 1024.0) / 1024.0
+    if scheme == "h2f8" or scheme.startswith("mix") or scheme.startswith("cal"):
+        return ah + e5m2(al * 1024.0) / 1024.0      # (cal: only used for the non-tcgen05 consumers; approximation)
+    if scheme == "h2f8v2":                       # candidate: e4m3 bytes with fixed exponents (al * 2^6, hi * 2^-5), saturating
+        return ah + e4m3(al * 64.0) / 64.0
     if scheme in ("h2f8e4", "h2f8e4b"):          # e4m3 residual with a static 2^9 scale (full precision for 2^-4 <= |x| < 2^11)
         return ah + e4m3(al * 512.0) / 512.0
     if scheme == "h2f8c":           # e5m2 residual, e4m3 copy of hi
         return ah + e5m2(al * 1024.0) / 1024.0
     raise ValueError(scheme)
+
+
+# ---- experimental (not shipped): e4m3 activation bytes with per-layer exponent windows from a calibration pass ----
+CAL = {"max": {}, "mode": None, "headroom": 4.0}      # layer index -> max |x| seen by that conv's input
+
+
+def e4m3_sat(t):
+    return t.to(torch.float32).clamp(-448, 448).to(torch.float8_e4m3fn).to(F64)
 
 
 def make_conv(scheme):
@@ -76,6 +86,33 @@ def make_conv(scheme):
         if mix_from is not None and cin % 64 == 0 and w.shape[0] % 64 == 0:
             scheme = "h2f8" if counter[0] < mix_from else "h2"
             counter[0] += 1
+        if scheme in ("cal", "calrec") and cin % 64 == 0 and w.shape[0] % 64 == 0:
+            li = counter[0]
+            counter[0] += 1
+            xt = torch.from_numpy(np.ascontiguousarray(x)).to(F64)
+            if scheme == "calrec":                     # calibration pass: record max |x| per layer, compute exactly
+                CAL["max"][li] = max(CAL["max"].get(li, 0.0), float(xt.abs().max()))
+                return real_conv(x, w, b, pad, stride, dilation, group, engine="torch")
+            xmax = CAL["max"][li] * CAL["headroom"]
+            # window: al <= 2^-11 * xmax -> al * 2^p <= 256 ; ah <= xmax -> ah * 2^-r <= 256
+            p_exp = math.floor(math.log2(256.0 / (xmax * 2.0 ** -11)))
+            r_exp = math.ceil(math.log2(xmax / 256.0))
+            wt = torch.from_numpy(np.ascontiguousarray(w)).to(F64)
+            k = int(14 - math.ceil(math.log2(float(wt.abs().max()))))
+            ws = wt * 2.0 ** k
+            cv = lambda a, bb: torch.nn.functional.conv2d(a, bb, None, stride=stride, padding=pad, dilation=dilation)
+            # the stored activation itself is ah + al8 / 2^p (what the previous layer wrote)
+            ah = rn16(xt)
+            al8 = e4m3_sat((xt - ah) * 2.0 ** p_exp)
+            ah8 = e4m3_sat(ah * 2.0 ** -r_exp)
+            wh = rn16(ws)
+            wl = ws - wh
+            wh8 = e4m3_sat(wh * 2.0 ** -p_exp) if p_exp <= 14 else e4m3_sat(wh * 2.0 ** -p_exp)
+            wl8 = e4m3_sat(wl * 2.0 ** r_exp)
+            y = (cv(ah, wh) + cv(al8, wh8) + cv(ah8, wl8)) * 2.0 ** (-k)
+            if b is not None:
+                y = y + torch.from_numpy(np.asarray(b)).to(F64)[None, :, None, None]
+            return y.to(torch.float32).numpy()
         if cin % 64 or w.shape[0] % 64 or scheme == "exact":          # conv1_1, cls/bbox 1x1: fp32 SIMT kernels
             xq = quant_act(torch.from_numpy(np.ascontiguousarray(x)), scheme if cin % 64 == 0 else "exact")
             return real_conv(xq.to(torch.float32).numpy(), w, b, pad, stride, dilation, group, engine="torch")
@@ -94,6 +131,8 @@ def make_conv(scheme):
         elif scheme == "h2":
             all_, wll = rn16(al), rn16(wl)
             y = cv(ah, wh) + cv(ah, wll) + cv(all_, wh)
+        elif scheme == "h2f8v2":
+            y = cv(ah, wh) + cv(e4m3(al * 64.0), e4m3(wh / 64.0)) + cv(e4m3(ah / 32.0), e4m3(wl * 32.0))
         elif scheme in ("h2f8", "h2f8e4", "h2f8e4b", "h2f8c"):
             if scheme == "h2f8":
                 al8 = e5m2(al * 1024.0)
