@@ -429,7 +429,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--fast-min-scale", default=None,
                     help="operand-format policy override for trade-off tables: a number, or 'none' for split fp16 on every "
-                         "level (default: DetectConfig's 1.3)")
+                         "level (default: DetectConfig's 0.9)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,12 +54,15 @@ inline const char* shf_probe_env(const char* name) {
 //      planes [2][N][H][W][C] of __half; the conv issues hi*hi + hi*lo + lo*hi as three kind::f16 MMAs.
 //
 //  SHF_FMT_HF8 ("hf8", fast): plane 0 = hi = rn_f16(x) as above; plane 1 holds, per pixel and per block of 64
-//      channels, 64 bytes  al8 = e5m2((x - hi) * 2^10)  followed by 64 bytes  ah8 = e5m2(hi)  -- i.e. one 128-byte
-//      K = 128 row of 8-bit floats.  The conv issues hi*hi as ONE kind::f16 MMA and the first-order correction
-//      al*wh + ah*wl as ONE kind::f8f6f4 MMA (K = 32 per instruction, same issue time) against a weight plane laid
-//      out the same way ([wh8 = e4m3(wh * 2^-10) | wl8 = e4m3(wl)]): 2 MMAs per 16 channels instead of 3.
-//      x is recovered as hi + al8 * 2^-10 (|err| <~ 2^-15 |x|); C must be a multiple of 64.
-//      tools/precision_model.py quantifies what that costs in box / score accuracy per pyramid level.
+//      channels, 64 bytes  al8 = e4m3((x - hi) * 2^6)  followed by 64 bytes  ah8 = e4m3(hi * 2^-5)  (saturating) -- i.e.
+//      one 128-byte K = 128 row of 8-bit floats.  The conv issues hi*hi as ONE kind::f16 MMA and the first-order
+//      correction al*wh + ah*wl as ONE kind::f8f6f4 MMA (K = 32 per instruction, same issue time) against a weight
+//      plane laid out the same way ([wh8 = e4m3(wh * 2^-6) | wl8 = e4m3(wl * 2^5)]): 2 MMAs per 16 channels, not 3.
+//      x is recovered as hi + al8 * 2^-6.  The fixed exponents give the residual its full 4 significant bits for
+//      2 <~ |x| < 16384 and hi its 4 bits for 0.5 <= |x| < 14336 (smaller values keep fewer bits -- their absolute
+//      error is negligible next to the large activations'; larger ones saturate towards plain-fp16 accuracy);
+//      C must be a multiple of 64.  tools/precision_model.py quantifies the accuracy per pyramid level (row h2f8v2; the
+//      range-free e5m2 variant h2f8 has 1.5x the error).
 // ----------------------------------------------------------------------------------------------
 enum { SHF_FMT_H2 = 0, SHF_FMT_HF8 = 1 };
 
@@ -69,16 +72,17 @@ SHF_DEVICE void split_h2(float v, __half& hi, __half& lo) {
 }
 SHF_DEVICE float join_h2(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 
-SHF_DEVICE uint8_t f32_to_e5m2(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); }
-// e5m2 is the upper byte of the fp16 with the same value
-SHF_DEVICE float e5m2_to_f32(uint8_t b) { return __half2float(__ushort_as_half((unsigned short)((unsigned short)b << 8))); }
+constexpr float kHf8AlScale = 64.f, kHf8AlInv = 0.015625f;       // al8 = e4m3(lo * 2^6)
+constexpr float kHf8AhScale = 0.03125f;                           // ah8 = e4m3(hi * 2^-5)
+SHF_DEVICE uint8_t f32_to_f8(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+SHF_DEVICE float f8_to_f32(uint8_t b) { return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3))); }
 SHF_DEVICE void split_hf8(float v, __half& hi, uint8_t& al8, uint8_t& ah8) {
   hi = __float2half_rn(v);
   const float h = __half2float(hi);
-  al8 = f32_to_e5m2((v - h) * 1024.f);
-  ah8 = f32_to_e5m2(h);
+  al8 = f32_to_f8((v - h) * kHf8AlScale);
+  ah8 = f32_to_f8(h * kHf8AhScale);
 }
-SHF_DEVICE float join_hf8(__half hi, uint8_t al8) { return fmaf(e5m2_to_f32(al8), 0.0009765625f, __half2float(hi)); }
+SHF_DEVICE float join_hf8(__half hi, uint8_t al8) { return fmaf(f8_to_f32(al8), kHf8AlInv, __half2float(hi)); }
 // byte offset of channel c's al8 inside a pixel's plane-1 row (its ah8 twin sits 64 bytes further)
 SHF_DEVICE int hf8_off(int c) { return ((c >> 6) << 7) + (c & 63); }
 
@@ -123,8 +127,10 @@ SHF_DEVICE void act_load8(const __half* px0, size_t plane_elems, int c, float (&
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 a = __half22float2(hh[j]);
-      v[2 * j] = fmaf(e5m2_to_f32(ab[2 * j]), 0.0009765625f, a.x);
-      v[2 * j + 1] = fmaf(e5m2_to_f32(ab[2 * j + 1]), 0.0009765625f, a.y);
+      const __half2_raw r2 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((unsigned short)ab[2 * j] | ((unsigned short)ab[2 * j + 1] << 8)), __NV_E4M3);
+      const float2 l2 = __half22float2(__half2(r2));
+      v[2 * j] = fmaf(l2.x, kHf8AlInv, a.x);
+      v[2 * j + 1] = fmaf(l2.y, kHf8AlInv, a.y);
     }
   }
 }
@@ -146,12 +152,13 @@ SHF_DEVICE void act_store8(__half* px0, size_t plane_elems, int c, const float (
     uint32_t ap[2] = {0u, 0u}, bp[2] = {0u, 0u};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      // pairs: one F2FP packs two fp16 / two e5m2 values
+      // pairs: one F2FP packs two fp16 / two e4m3 values
       const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
       const float2 hf = __half22float2(h);
-      const float2 lo = make_float2((v[2 * e] - hf.x) * 1024.f, (v[2 * e + 1] - hf.y) * 1024.f);
-      const uint32_t a2 = (uint32_t)__nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E5M2);
-      const uint32_t b2 = (uint32_t)__nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E5M2);
+      const float2 lo = make_float2((v[2 * e] - hf.x) * kHf8AlScale, (v[2 * e + 1] - hf.y) * kHf8AlScale);
+      const float2 hs = make_float2(hf.x * kHf8AhScale, hf.y * kHf8AhScale);
+      const uint32_t a2 = (uint32_t)__nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E4M3);
+      const uint32_t b2 = (uint32_t)__nv_cvt_float2_to_fp8x2(hs, __NV_SATFINITE, __NV_E4M3);
       hp[e] = *reinterpret_cast<const uint32_t*>(&h);
       ap[e >> 1] |= a2 << (16 * (e & 1));
       bp[e >> 1] |= b2 << (16 * (e & 1));

@@ -186,7 +186,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== MMA issuer (warp converged, one elected lane issues; leader CTA only) =====================
     constexpr uint32_t idesc_wide = umma_idesc_f16(kTileM * CTAS, 2 * BN);     // A_hi x [B_hi ; B_lo]      (CTAS == 1)
     constexpr uint32_t idesc_half = umma_idesc_f16(kTileM * CTAS, BN);         // one operand-plane pair
-    constexpr uint32_t idesc_f8 = umma_idesc_f8(kTileM * CTAS, BN, 1u, 0u);    // A = e5m2 activations, B = e4m3 weights
+    constexpr uint32_t idesc_f8 = umma_idesc_f8(kTileM * CTAS, BN, 0u, 0u);    // A and B = e4m3 (format code 0)
     const uint32_t a_hi32 = (uint32_t)((p.xw * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
     constexpr uint32_t b_hi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t lbo = 1u << 16;

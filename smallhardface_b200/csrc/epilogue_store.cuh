@@ -47,7 +47,7 @@ SHF_DEVICE void store_plane(uint8_t* stg, int lane, bool lane_writes, int lane_r
         }
         RS::put(stg, lane_row, k, make_uint4(w[0], w[1], w[2], w[3]));
       }
-    } else {                                                 // hf8 plane 1: [KC x e5m2((x - hi) * 2^10) | KC x e5m2(hi)]
+    } else {                                                 // hf8 plane 1: [KC x e4m3((x - hi) * 2^6) | KC x e4m3(hi * 2^-5)]
 #pragma unroll
       for (int k = 0; k < KC / 16; ++k) {
         uint32_t wa[4], wb[4];
@@ -58,9 +58,10 @@ SHF_DEVICE void store_plane(uint8_t* stg, int lane, bool lane_writes, int lane_r
           for (int q = 0; q < 2; ++q) {
             const float a = v[16 * k + 4 * e + 2 * q], b = v[16 * k + 4 * e + 2 * q + 1];
             const float2 hf = __half22float2(__floats2half2_rn(a, b));
-            const float2 lo = make_float2((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
-            a4 |= (uint32_t)__nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E5M2) << (16 * q);
-            b4 |= (uint32_t)__nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E5M2) << (16 * q);
+            const float2 lo = make_float2((a - hf.x) * kHf8AlScale, (b - hf.y) * kHf8AlScale);
+            const float2 hs = make_float2(hf.x * kHf8AhScale, hf.y * kHf8AhScale);
+            a4 |= (uint32_t)__nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E4M3) << (16 * q);
+            b4 |= (uint32_t)__nv_cvt_float2_to_fp8x2(hs, __NV_SATFINITE, __NV_E4M3) << (16 * q);
           }
           wa[e] = a4;
           wb[e] = b4;

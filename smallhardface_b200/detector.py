@@ -42,7 +42,7 @@ class DetectConfig:
     max_dets_out: int = 4096                                   # rows returned per image (post vote / NMS)
     # not a reference key: pyramid levels with im_scale >= this run the convs on the fast f16+f8 operand format, smaller
     # (error-magnifying) levels on precise split fp16; None = precise everywhere (see GpuNet / tools/precision_model.py)
-    fast_min_scale: float | None = 1.3
+    fast_min_scale: float | None = 0.9
 
 
 def compute_scaling_factor(im_shape, target_size, max_size):

@@ -27,9 +27,9 @@ from .graph import NetSpec, TEST as _TEST, TRAIN as _TRAIN, load_weights
 TRAIN, TEST = _TRAIN, _TEST
 def _env_fast_min_scale():
     """SHF_FAST_MIN_SCALE: 'none' = split-fp16 operands for every forward, a number = the im_info scale from which
-    the fast f16+f8 operand format is used (default 1.3, see engine.GpuNet)."""
+    the fast f16+f8 operand format is used (default 0.9, see engine.GpuNet)."""
     import os
-    v = os.environ.get("SHF_FAST_MIN_SCALE", "1.3").strip().lower()
+    v = os.environ.get("SHF_FAST_MIN_SCALE", "0.9").strip().lower()
     return None if v in ("none", "off", "") else float(v)
 
 

@@ -203,8 +203,10 @@ def test_deconv_depthwise_into_concat_window():
 # ---------------------------------------------------------------------------------------------------------------
 # fast operand format "hf8" (fp16 hi plane + 8-bit-float correction plane, include/shf_b200.h)
 # ---------------------------------------------------------------------------------------------------------------
-def _e5m2(a):
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=F32)).to(torch.float8_e5m2).to(torch.float32).numpy()
+def _e4m3(a):
+    """float32 -> e4m3 -> float32 the way cvt.rn.satfinite.e4m3x2.f32 does it (round to nearest even, saturate at 448)."""
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=F32)).clamp(-448.0, 448.0)
+    return t.to(torch.float8_e4m3fn).to(torch.float32).numpy()
 
 
 def _e4m3_bytes_to_f32(b):
@@ -212,21 +214,22 @@ def _e4m3_bytes_to_f32(b):
 
 
 def hf8_planes_np(x):
-    """(hi as f32, al8 * 2^-10... as the three operand planes the tensor core sees: ah, al8 (scaled by 2^10), ah8)"""
+    """The three operand planes the tensor core sees: ah (fp16), al8 = e4m3((x - ah) * 2^6), ah8 = e4m3(ah * 2^-5)."""
     x = np.asarray(x, F32)
     ah = x.astype(np.float16).astype(F32)
-    al8 = _e5m2((x - ah) * F32(1024.0))
-    ah8 = _e5m2(ah)
+    al8 = _e4m3((x - ah) * F32(64.0))
+    ah8 = _e4m3(ah * F32(0.03125))
     return ah, al8, ah8
 
 
 def hf8_roundtrip_np(x):
     ah, al8, _ = hf8_planes_np(x)
-    return (ah.astype(np.float64) + al8.astype(np.float64) / 1024.0).astype(F32)
+    return (ah.astype(np.float64) + al8.astype(np.float64) / 64.0).astype(F32)
 
 
 def hf8_conv_model(x, packed8, kexp, cout, cin, k, pad, dil, bias, relu):
-    """What the fast conv computes, in float64: ah*wh + (al8*wh8 + ah8*wl8), all at scale 2^kexp."""
+    """What the fast conv computes, in float64: ah*wh + (al8*wh8 + ah8*wl8), all at scale 2^kexp (al8 carries 2^6 and
+    wh8 2^-6, ah8 2^-5 and wl8 2^5: the products are at the scale of the main term)."""
     ah, al8, ah8 = hf8_planes_np(x)
     wh = packed8[0].astype(np.float64).reshape(k, k, cout, cin).transpose(2, 3, 0, 1)
     p1 = _e4m3_bytes_to_f32(packed8[1].view(np.uint8)).reshape(k * k, cout, cin // 64, 2, 64)
@@ -250,11 +253,11 @@ def test_hf8_roundtrip():
     back = t.to_nchw().cpu().numpy()
     assert np.array_equal(back, hf8_roundtrip_np(x))
     assert relerr(back, x) < 2 ** -14
-    # plane 1 really holds [64 x e5m2(lo * 2^10) | 64 x e5m2(hi)] per pixel and 64-channel block
+    # plane 1 really holds [64 x e4m3(lo * 2^6) | 64 x e4m3(hi * 2^-5)] per pixel and 64-channel block
     p1 = t.t[1].view(torch.uint8).reshape(2, 9, 13, 2, 2, 64).cpu()
     ah, al8, ah8 = hf8_planes_np(x)
-    got_al8 = p1[:, :, :, :, 0].view(torch.float8_e5m2).to(torch.float32).numpy().reshape(2, 9, 13, 128).transpose(0, 3, 1, 2)
-    got_ah8 = p1[:, :, :, :, 1].view(torch.float8_e5m2).to(torch.float32).numpy().reshape(2, 9, 13, 128).transpose(0, 3, 1, 2)
+    got_al8 = p1[:, :, :, :, 0].contiguous().view(torch.float8_e4m3fn).to(torch.float32).numpy().reshape(2, 9, 13, 128).transpose(0, 3, 1, 2)
+    got_ah8 = p1[:, :, :, :, 1].contiguous().view(torch.float8_e4m3fn).to(torch.float32).numpy().reshape(2, 9, 13, 128).transpose(0, 3, 1, 2)
     assert np.array_equal(got_al8, al8) and np.array_equal(got_ah8, ah8)
 
 
