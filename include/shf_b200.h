@@ -10,8 +10,9 @@
  *   SHF_FMT_H2  (0, "h2", precise): planes [2][N][H][W][C] of __half with x = hi + lo (hi = rn(x), lo = rn(x - hi));
  *               C a multiple of 8 (16-byte rows for TMA).  The conv runs 3 fp16 MMAs per 16 input channels.
  *   SHF_FMT_HF8 (1, "hf8", fast): plane 0 = hi as above; plane 1 = per pixel and 64-channel block, 64 bytes
- *               e5m2((x - hi) * 2^10) then 64 bytes e5m2(hi); C (and channel windows) multiples of 64.  The conv
- *               runs 1 fp16 + 1 fp8 (K = 32) MMA per 16 input channels; x is carried to ~2^-15 relative.
+ *               e4m3((x - hi) * 2^6) then 64 bytes e4m3(hi * 2^-5), both saturating; C (and channel windows) multiples
+ *               of 64.  The conv runs 1 fp16 + 1 fp8 (K = 32) MMA per 16 input channels; x = hi + al8 * 2^-6 is carried
+ *               to ~2^-16 relative for 2 <~ |x| < 16384 (fewer residual bits below, saturation above).
  * Each declaration cites the reference interface it stands in for (paths under the reference repo).
  */
 #ifndef SHF_B200_H
@@ -36,7 +37,7 @@ int shf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, lon
  * in-place ReLULayer (relu_layer.cpp:9-19), for 3x3 (pad == dilation, stride 1) and 1x1 convolutions with
  * Cin, Cout multiples of 64.  tcgen05 implicit GEMM.  w_h2 [dev]: weights pre-packed as
  * [2 planes][taps][Cout][Cin] fp16 of (w * 2^k) (in_format h2: hi / lo planes; in_format hf8: plane 1 holds, per
- * (tap, Cout, 64-channel block), 64 bytes e4m3(hi * 2^-10) then 64 bytes e4m3(lo)); out_scale = 2^-k.
+ * (tap, Cout, 64-channel block), 64 bytes e4m3(hi * 2^-6) then 64 bytes e4m3(lo * 2^5)); out_scale = 2^-k.
  * in_format describes in_h2 AND w_h2, out_format what is written.  The result lands in channels
  * [out_channel_offset, +cout) of an h2 tensor with out_channels_total channels (ConcatLayer by construction,
  * concat_layer.cpp:47-74). */

@@ -8,10 +8,12 @@ schemes:
   exact      fp32 operands (yardstick against itself: 0)
   f16        single fp16 operand planes                       x ~ rn16(x), w ~ rn16(w)
   h2         split fp16 (hi + lo, 3 MMAs: hi*hi + hi*lo + lo*hi)
-  h2f8       fp16 main term + fp8 correction term:
-               x = ah + al,  ah = rn16(x),  al8 = e5m2(al * 2^10),  ah8 = e5m2(ah)
-               w*2^k = wh + wl, wh = rn16,  wh8 = e4m3(wh * 2^-10), wl8 = e4m3(wl)
+  h2f8v2     SHIPPED hf8: fp16 main term + fp8 correction term with fixed exponents:
+               x = ah + al,  ah = rn16(x),  al8 = e4m3(al * 2^6),  ah8 = e4m3(ah * 2^-5)
+               w*2^k = wh + wl, wh = rn16,  wh8 = e4m3(wh * 2^-6), wl8 = e4m3(wl * 2^5)
                y = ah*wh  +  al8*wh8 + ah8*wl8        (one kind::f16 MMA + one K=32 kind::f8f6f4 MMA per 16 channels)
+  h2f8       the first version: e5m2 activation bytes (al * 2^10, ah), weights e4m3(wh * 2^-10), e4m3(wl)
+  h2f8c / h2f8e4 / h2f8e4b / cal   other e4m3 windows, incl. per-layer calibrated ones (study only)
 
 usage: python tools/precision_model.py [level ...]      (levels = TEST.SCALES entries, default 100 300)
 """
