@@ -183,6 +183,33 @@ def test_batchnorm_scale_fold_equals_layerwise_oracle():
     assert np.abs(y2 - out["c2_out"]).max() <= 2e-5 * np.abs(y2).max()
 
 
+def test_precision_model_scheme_equals_the_packed_operands():
+    """tools/precision_model.py's `h2f8v2` scheme (the accuracy evidence in DESIGN.md) multiplies exactly the operands that
+    engine.pack_conv_weights_hf8 ships and that the kernels' hf8 activation format stores."""
+    import importlib.util
+    import torch
+    from smallhardface_b200.engine import pack_conv_weights_hf8
+    spec = importlib.util.spec_from_file_location("precision_model", os.path.join(ROOT, "tools", "precision_model.py"))
+    pm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pm)
+    rng = np.random.RandomState(9)
+    x = (np.abs(rng.randn(1, 64, 6, 7)) * 30).astype(np.float32)
+    w = (rng.randn(64, 64, 3, 3) * 0.04).astype(np.float32)
+    y_model = pm.make_conv("h2f8v2")(x, w, None, pad=(1, 1))
+    packed, k = pack_conv_weights_hf8(w)
+    e4 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).clamp(-448, 448).to(torch.float8_e4m3fn).to(torch.float64)
+    xt = torch.from_numpy(x).to(torch.float64)
+    ah = xt.to(torch.float16).to(torch.float64)
+    al8, ah8 = e4((xt - ah) * 64.0), e4(ah / 32.0)
+    wh = torch.from_numpy(packed[0].astype(np.float64)).reshape(3, 3, 64, 64).permute(2, 3, 0, 1).contiguous()
+    p1 = torch.from_numpy(packed[1].view(np.uint8).copy()).view(torch.float8_e4m3fn).to(torch.float64).reshape(9, 64, 1, 2, 64)
+    wh8 = p1[:, :, :, 0].reshape(3, 3, 64, 64).permute(2, 3, 0, 1).contiguous()
+    wl8 = p1[:, :, :, 1].reshape(3, 3, 64, 64).permute(2, 3, 0, 1).contiguous()
+    cv = lambda a, b: torch.nn.functional.conv2d(a, b, None, padding=1)
+    y = ((cv(ah, wh) + cv(al8, wh8) + cv(ah8, wl8)) * 2.0 ** -k).to(torch.float32).numpy()
+    assert np.array_equal(y, y_model)
+
+
 # ---- caffe / caffe_pb2 shims ---------------------------------------------------------------------
 def test_caffe_pb2_shim_text_and_wire():
     from smallhardface_b200 import compat
