@@ -40,10 +40,15 @@ int shf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, lon
  * (tap, Cout, 64-channel block), 64 bytes e4m3(hi * 2^-6) then 64 bytes e4m3(lo * 2^5)); out_scale = 2^-k.
  * in_format describes in_h2 AND w_h2, out_format what is written.  The result lands in channels
  * [out_channel_offset, +cout) of an h2 tensor with out_channels_total channels (ConcatLayer by construction,
- * concat_layer.cpp:47-74). */
+ * concat_layer.cpp:47-74).
+ * range_guard [dev, may be NULL]: one 32-bit slot that receives (atomic max) the float bits of max |x| over the values
+ * this launch writes.  The fixed exponent windows of the hf8 format and the fp16 range of either format make that the
+ * quantity a caller must watch on weights it has not seen: >= 65504 overflows hi, >= 14336 saturates the hf8 ah8 bytes,
+ * a small maximum (< ~32) leaves the hf8 residual bytes fewer than their 4 bits.  shf_conv1_tc and
+ * shf_deconv_depthwise take the same argument. */
 int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                    int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
-                   float out_scale, int relu, int in_format, int out_format, void* stream);
+                   float out_scale, int relu, int in_format, int out_format, unsigned int* range_guard, void* stream);
 
 /* shf_conv_igemm + the PoolingLayer MAX 2x2/2 that follows it (pooling_layer.cpp:140-187) in one launch: the pooled
  * map goes to pool_out_h2 (N, H/2, W/2, pool_channels_total) at pool_channel_offset; out_h2 may be NULL when the
@@ -51,11 +56,10 @@ int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void*
 int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, void* pool_out_h2, int batch,
                         int H, int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
                         int out_channel_offset, int pool_channels_total, int pool_channel_offset, float out_scale,
-                        int relu, int in_format, int out_format, void* stream);
+                        int relu, int in_format, int out_format, unsigned int* range_guard, void* stream);
 
-/* Tuning / test hook: selects the kernel behind shf_conv_igemm (same results): 0 = v1, one TMA load per (tap, chunk);
- * 1-5 = v2 halo-tile variants; 7 = v3 persistent streaming-drain kernel, one CTA per tile; 8 = v3 on CTA pairs
- * (tcgen05 cta_group::2, the default).  0-5 only know the h2 format. */
+/* Test hook: 8 = the conv kernel on CTA pairs (tcgen05 cta_group::2, the product path and the default), 7 = the same
+ * persistent streaming-drain kernel with one CTA per tile (regression twin of the pair protocol; same results). */
 int shf_set_conv_impl(int impl);
 
 /* conv1_1: fp32 NCHW (N,3,H,W) [dev] -> h2 (N,H,W,64); weights OIHW fp32 [dev] (64,3,3,3), pad 1. */
@@ -67,7 +71,7 @@ int shf_conv1_c3(const float* in_nchw, const float* w_oihw, const float* bias, v
  * w_packed [dev]: fp16 [2][64][64] of (w * 2^k): [0] = rows [hi(32) | hi(32)], [1] = rows [lo(32) | 0], K index
  * c*9 + r*3 + s padded to 32; out_scale = 2^-k. */
 int shf_conv1_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H, int W,
-                 int cout, float out_scale, int relu, int out_format, void* stream);
+                 int cout, float out_scale, int relu, int out_format, unsigned int* range_guard, void* stream);
 
 /* PoolingLayer MAX 2x2 stride 2 (pooling_layer.cpp:79-123,140-187), ceil-mode output (H+1)/2 x (W+1)/2. */
 int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int C, int format, void* stream);
@@ -76,7 +80,7 @@ int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H, int W, int
  * w [dev]: fp32 (C,1,k,k). Output size stride*(H-1)+k-2*pad, written at a channel offset like shf_conv_igemm. */
 int shf_deconv_depthwise(const void* in_h2, const float* w, void* out_h2, int batch, int H, int W, int C, int ksize,
                          int stride, int pad, int out_channels_total, int out_channel_offset, int in_format,
-                         int out_format, void* stream);
+                         int out_format, unsigned int* range_guard, void* stream);
 
 /* Blob boundary (caffe/python/caffe/_caffe.cpp:205-242 exposes blobs as fp32 NCHW arrays). */
 int shf_h2_to_nchw(const void* in_h2, float* out_nchw, int batch, int H, int W, int channels_total, int channel_offset,

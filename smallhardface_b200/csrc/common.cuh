@@ -171,6 +171,21 @@ SHF_DEVICE void act_store8(__half* px0, size_t plane_elems, int c, const float (
 }
 
 // ----------------------------------------------------------------------------------------------
+// Range guard: every kernel that WRITES an activation tensor can publish max |x| of what it wrote (float bits of a
+// non-negative value order like unsigned integers) into one 32-bit slot.  The host reads the slots at its next
+// synchronisation point: a value >= 65504 means the fp16 hi plane overflowed (either format); for hf8 tensors a value
+// >= 14336 means the ah8 = e4m3(hi * 2^-5) bytes saturated and a small maximum means the residual bytes
+// e4m3((x - hi) * 2^6) have underflowed their 4 significant bits -- the caller then repeats the level on split fp16
+// (smallhardface_b200/engine.py: GpuNet.check_ranges).  One warp-level reduction + at most one atomic per warp per
+// launch: call once, warp-converged, after the kernel's persistent / grid-stride loop.
+// ----------------------------------------------------------------------------------------------
+SHF_DEVICE void range_guard_commit(unsigned int* guard, float thread_abs_max) {
+  if (guard == nullptr) return;
+  const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(thread_abs_max));
+  if ((threadIdx.x & 31) == 0 && m > *reinterpret_cast<volatile unsigned int*>(guard)) atomicMax(guard, m);
+}
+
+// ----------------------------------------------------------------------------------------------
 // PTX wrappers
 // ----------------------------------------------------------------------------------------------
 SHF_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

@@ -26,6 +26,7 @@ struct C1Params {
   int N, H, W, relu, out_fmt;
   int tiles_x, tiles_y, total_tiles;
   float out_scale;          // 2^-k
+  unsigned int* guard;      // range guard slot or nullptr (common.cuh)
 };
 
 constexpr int kC1Threads = 128;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
   const uint64_t b2_desc = umma_desc_sw128(smem_base + 24576);
   const bool issuer = (warp == 0) && elect_one();
   uint32_t phase = 0;
+  float gmax = 0.f;
 
   for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
     int q = t;
@@ -145,6 +147,10 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
 #pragma unroll
       for (int e = 0; e < 64; ++e) v[e] = fmaxf(v[e], 0.f);
     }
+    if (p.guard && y < p.H && x < p.W) {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) gmax = fmaxf(gmax, fabsf(v[e]));
+    }
     uint8_t* stg = stage_s + warp * 4096;
     const int qy = y0 + warp * 4;
     auto dst = [&](int row) -> __half* {
@@ -154,6 +160,7 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
     store_plane<64>(stg, lane, true, lane, 32, v, 0, p.out_fmt, 0, (size_t)p.plane_elems, dst);
     store_plane<64>(stg, lane, true, lane, 32, v, 1, p.out_fmt, 0, (size_t)p.plane_elems, dst);
   }
+  range_guard_commit(p.guard, gmax);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -166,7 +173,8 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
 
 // C ABI -- see include/shf_b200.h
 extern "C" int shf_conv1_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch,
-                            int H, int W, int cout, float out_scale, int relu, int out_format, void* stream) {
+                            int H, int W, int cout, float out_scale, int relu, int out_format,
+                            unsigned int* range_guard, void* stream) {
   SHF_REQUIRE(cout == 64, "shf_conv1_tc: Cout=%d (the deploy nets' conv1_1 has 64)", cout);
   SHF_REQUIRE(out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8, "shf_conv1_tc: unknown activation format %d", out_format);
   SHF_REQUIRE(batch >= 1 && H >= 1 && W >= 1, "shf_conv1_tc: bad geometry");
@@ -181,6 +189,7 @@ extern "C" int shf_conv1_tc(const float* in_nchw, const void* w_packed, const fl
   p.tiles_y = (H + kTH - 1) / kTH;
   p.total_tiles = p.tiles_x * p.tiles_y * batch;
   p.out_scale = out_scale;
+  p.guard = range_guard;
   const int smem_bytes = 1024 + 49152 + 16 + 256;
   static bool attr = false;
   if (!attr) {

@@ -1,7 +1,9 @@
 // Implicit-GEMM convolution v3 on tcgen05 tensor cores (sm_100a): persistent CTAs, halo-tile operand reuse, and
 // accumulators that are DRAINED into registers every few dozen MMAs while the tensor pipe keeps running.
 //
-// Same math / layout / reference citations as conv_igemm.cu and conv_halo.cu.  What v3 changes, and why
+// Replaces ConvolutionLayer<float>::Forward (conv_layer.cpp:30-46 -> base_conv_layer.cpp:255-279: im2col + sgemm) and
+// the in-place ReLU / 2x2 max pooling that follow it.  The round-1 predecessors (one TMA load per (tap, chunk); a
+// non-persistent halo-tile kernel) are gone from the tree; what this kernel does differently from them, and why
 // (numbers from profiles/r01_*):
 //  * persistent: one CTA per SM walks tiles t = blockIdx.x + i*gridDim.x.  v2 paid ~15k cycles per tile for CTA
 //    launch, barrier init, TMEM alloc, first-load latency and a serial epilogue; here the TMA rings simply keep
@@ -59,6 +61,7 @@ struct StreamParams {
   __half* pool_out;           // nullptr: no pooling
   long long pool_plane_elems;
   int pool_ctot, pool_coffset;
+  unsigned int* guard;        // range guard slot (max |x| written, float bits) or nullptr
 };
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -291,6 +294,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t drained0 = (CTAS == 2) ? mapa_shared(acc_empty(0), 0) : acc_empty(0);   // in the leader
     const uint32_t drained1 = (CTAS == 2) ? mapa_shared(acc_empty(1), 0) : acc_empty(1);
     int gp = 0, tile_it = 0;
+    float gmax = 0.f;                            // range guard: max |x| this thread has written
     for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
       int nt, x0, y0, img;
       decode_tile(t, nt, x0, y0, img);
@@ -347,6 +351,10 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         acc[c] = fmaf(acc[c], scale, bias_t[col0 + c]);
         if (p.relu) acc[c] = fmaxf(acc[c], 0.f);
       }
+      if (p.guard && inside) {
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) gmax = fmaxf(gmax, fabsf(acc[c]));
+      }
       uint8_t* stg = stage_s + w * 4096;
       const int c_first = n0 + col0;
       if (p.out && (p.probe & 3) != 1) {
@@ -382,6 +390,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       }
     }
+    range_guard_commit(p.guard, gmax);
   }
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
@@ -433,10 +442,10 @@ int sm_count() {
 
 }  // namespace
 
-int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
+static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
-                         int ctas, int in_format, int out_format, void* stream) {
+                         int ctas, int in_format, int out_format, unsigned int* range_guard, void* stream) {
   SHF_REQUIRE(ctas == 1 || ctas == 2, "shf_conv_igemm: %d CTAs per tile group", ctas);
   SHF_REQUIRE((in_format == SHF_FMT_H2 || in_format == SHF_FMT_HF8) && (out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8),
               "shf_conv_igemm: unknown activation format %d / %d", in_format, out_format);
@@ -504,6 +513,7 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   p.pool_plane_elems = (long long)batch * (H / 2) * (W / 2) * pool_channels_total;
   p.pool_ctot = pool_channels_total;
   p.pool_coffset = pool_channel_offset;
+  p.guard = range_guard;
   const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 1536 + 8 * 4096;
 
   CUtensorMap ta, tb;
@@ -523,4 +533,37 @@ int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias,
   if (ctas == 2)
     return bn == 128 ? launch_stream<128, 2>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64, 2>(ta, tb, p, smem_bytes, grid, st);
   return bn == 128 ? launch_stream<128, 1>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64, 1>(ta, tb, p, smem_bytes, grid, st);
+}
+
+// ---- C ABI (include/shf_b200.h) ---------------------------------------------------------------------------------
+static int g_conv_ctas = 2;
+
+// 8 = CTA pairs (tcgen05 cta_group::2, the product path), 7 = the same kernel with one CTA per tile (kept as the
+// regression twin of the pair protocol: same math, no cluster).
+extern "C" int shf_set_conv_impl(int impl) {
+  SHF_REQUIRE(impl == 7 || impl == 8, "shf_set_conv_impl: %d (7 = single CTA, 8 = CTA pairs)", impl);
+  g_conv_ctas = impl == 7 ? 1 : 2;
+  return 0;
+}
+
+extern "C" int shf_conv_igemm(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H,
+                              int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
+                              int out_channel_offset, float out_scale, int relu, int in_format, int out_format,
+                              unsigned int* range_guard, void* stream) {
+  return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
+                              out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_ctas, in_format, out_format,
+                              range_guard, stream);
+}
+
+// Convolution + ReLU + 2x2/2 max pooling in one launch.  out_h2 may be NULL when only the pooled map is consumed
+// downstream (conv1_2, conv2_2, conv3_3 of VGG16); conv4_3 needs both.
+extern "C" int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, void* pool_out_h2,
+                                   int batch, int H, int W, int cin, int cout, int ksize, int dilation,
+                                   int out_channels_total, int out_channel_offset, int pool_channels_total,
+                                   int pool_channel_offset, float out_scale, int relu, int in_format, int out_format,
+                                   unsigned int* range_guard, void* stream) {
+  SHF_REQUIRE(pool_out_h2 != nullptr, "shf_conv_igemm_pool: pool_out_h2 is NULL");
+  return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
+                              out_channel_offset, out_scale, relu, pool_out_h2, pool_channels_total,
+                              pool_channel_offset, g_conv_ctas, in_format, out_format, range_guard, stream);
 }

@@ -152,10 +152,11 @@ __global__ void __launch_bounds__(256) maxpool2x2_h2_kernel(const __half* __rest
 __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                            __half* __restrict__ out, int N, int H, int W, int C,
                                                            int K, int S, int P, int HO, int WO, int CT, int c_off,
-                                                           int in_fmt, int out_fmt) {
+                                                           int in_fmt, int out_fmt, unsigned int* guard) {
   const int cv = C / 8;
   const long long total = (long long)N * HO * WO * cv;
   const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * CT;
+  float gmax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cv);
@@ -181,8 +182,11 @@ __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restr
         for (int j = 0; j < 8; ++j) acc[j] += v[j] * __ldg(w + ((size_t)(c8 * 8 + j) * K + ky) * K + kx);
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gmax = fmaxf(gmax, fabsf(acc[j]));
     act_store8(out + (((size_t)n * HO + oy) * WO + ox) * CT, out_plane, c_off + c8 * 8, acc, out_fmt);
   }
+  range_guard_commit(guard, gmax);
 }
 
 // Fast path for the net's own upsampler (k = 4, stride 2, pad 1): every output pixel has exactly 2 x 2 taps,
@@ -191,7 +195,8 @@ __global__ void __launch_bounds__(256) deconv_dw_h2_kernel(const __half* __restr
 // (ky ascending, then kx ascending) is the same as the generic kernel / col2im.
 __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                                __half* __restrict__ out, int N, int H, int W, int C,
-                                                               int CT, int c_off, int in_fmt, int out_fmt) {
+                                                               int CT, int c_off, int in_fmt, int out_fmt,
+                                                               unsigned int* guard) {
   extern __shared__ float wsm[];                 // [16 taps][C]: a warp's lanes (consecutive 8-channel groups) read
                                                  // consecutive 32-byte runs (the [C][16] layout was a 32-way bank conflict)
   for (int i = threadIdx.x; i < C * 16; i += blockDim.x) wsm[(i & 15) * C + (i >> 4)] = w[i];
@@ -199,6 +204,7 @@ __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __r
   const int HO = 2 * H, WO = 2 * W, cv = C / 8;
   const long long total = (long long)N * HO * WO * cv;
   const size_t in_plane = (size_t)N * H * W * C, out_plane = (size_t)N * HO * WO * CT;
+  float gmax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cv);
@@ -227,8 +233,11 @@ __global__ void __launch_bounds__(256) deconv_k4s2p1_h2_kernel(const __half* __r
         acc[4] += v[4] * w1.x; acc[5] += v[5] * w1.y; acc[6] += v[6] * w1.z; acc[7] += v[7] * w1.w;
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gmax = fmaxf(gmax, fabsf(acc[j]));
     act_store8(out + (((size_t)n * HO + oy) * WO + ox) * CT, out_plane, c_off + c8 * 8, acc, out_fmt);
   }
+  range_guard_commit(guard, gmax);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -405,7 +414,7 @@ extern "C" int shf_maxpool2x2(const void* in_h2, void* out_h2, int batch, int H,
 
 extern "C" int shf_deconv_depthwise(const void* in_h2, const float* w, void* out_h2, int batch, int H, int W, int C,
                                     int ksize, int stride, int pad, int out_channels_total, int out_channel_offset,
-                                    int in_format, int out_format, void* stream) {
+                                    int in_format, int out_format, unsigned int* range_guard, void* stream) {
   SHF_REQUIRE(C % 8 == 0 && out_channel_offset % 8 == 0 && out_channels_total % 8 == 0,
               "shf_deconv_depthwise: channel counts must be multiples of 8");
   SHF_REQUIRE((in_format == SHF_FMT_H2 || (in_format == SHF_FMT_HF8 && C % 64 == 0)) &&
@@ -417,13 +426,13 @@ extern "C" int shf_deconv_depthwise(const void* in_h2, const float* w, void* out
   if (ksize == 4 && stride == 2 && pad == 1 && C * 16 * sizeof(float) <= 48 * 1024) {
     deconv_k4s2p1_h2_kernel<<<grid_for(total, 256), 256, C * 16 * sizeof(float), (cudaStream_t)stream>>>(
         (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, out_channels_total, out_channel_offset, in_format,
-        out_format);
+        out_format, range_guard);
     SHF_LAUNCH_CHECK();
     return 0;
   }
   deconv_dw_h2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)in_h2, w, (__half*)out_h2, batch, H, W, C, ksize, stride, pad, HO, WO, out_channels_total,
-      out_channel_offset, in_format, out_format);
+      out_channel_offset, in_format, out_format, range_guard);
   SHF_LAUNCH_CHECK();
   return 0;
 }

@@ -113,6 +113,17 @@ def pack_conv1_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
 
 FMT_H2, FMT_HF8 = L.FMT_H2, L.FMT_HF8
 
+# Range guard thresholds (see include/shf_b200.h, `range_guard`): max |x| of every activation tensor a launch writes.
+F16_MAX = 65504.0          # hi = rn_f16(x) overflows above this in EITHER format: the forward is invalid -> raise
+HF8_SATURATION = 14336.0   # ah8 = e4m3(hi * 2^-5) saturates at 448 * 32: the correction term is wrong above this
+HF8_MIN_TENSOR_MAX = 32.0  # al8 = e4m3((x - hi) * 2^6) keeps 4 significant bits for |x| >~ 2; a tensor whose LARGEST value
+                           # is below 32 (typical values below ~4) carries its residuals with fewer bits than the policy
+                           # was validated for (the synthetic and VGG-like nets sit at 300..1400)
+
+
+class RangeError(L.ShfError):
+    """An activation exceeded the fp16 range of the operand formats (no valid result exists on this path)."""
+
 
 class H2:
     """NHWC activation tensor in one of the two 4-byte formats of include/shf_b200.h (``fmt``): torch.float16
@@ -216,6 +227,11 @@ class GpuNet:
             if l.type == "Python":
                 if (l.p["module"], l.p["layer"]) != ("lib.layers.proposal_layer", "ProposalLayer"):
                     raise L.ShfError("Python layer %s.%s has no CUDA implementation on this path" % (l.p["module"], l.p["layer"]))
+                if self.tail is not None:
+                    # the reference's multi-module form (boxes_<level> / cls_prob_<level>, lib/test.py:67-106) is not deployed
+                    # by any shipped config; refuse it instead of silently keeping the last ProposalLayer
+                    raise L.ShfError("more than one ProposalLayer (%s and %s): multi-module nets are not on this path"
+                                     % (self.tail["name"], l.name))
                 self.tail = self._plan_tail(l, params, fused)
         # ---- concat-by-offset ------------------------------------------------------------------------
         self.concat_dst: Dict[str, Tuple[str, int, int]] = {}
@@ -332,6 +348,15 @@ class GpuNet:
             else:
                 raise L.ShfError("layer %s of type %s has no CUDA implementation on this path" % (l.name, l.type))
             i += 1
+        # one range-guard slot per launch that writes an activation tensor; row 0 = written as h2, row 1 = as hf8
+        self.guard_ops = [(k, l.name) for k, l, st in self.ops if k in ("conv1", "conv", "deconv")]
+        n = 0
+        for k, l, st in self.ops:
+            if k in ("conv1", "conv", "deconv"):
+                st["slot"] = n
+                n += 1
+        self.guard = torch.zeros((2, max(n, 1)), dtype=torch.int32, device=dev)
+        self.fast_disabled = False        # set once a fast-format level tripped the guard: everything runs split fp16 after
 
     def _plan_tail(self, prop: LayerSpec, params, fused) -> dict:
         spec = self.spec
@@ -348,6 +373,10 @@ class GpuNet:
         A = anchors.shape[0]
         if lp.get("num_feats", 1) != 1 or len(prop.bottoms) != 3:
             raise L.ShfError("ProposalLayer with refinement bottoms / num_feats != 1 is not on the test path")
+        if len(set(int(v) for v in lp["feat_stride"])) != 1:
+            # unequal strides make proposal_layer.py:160-169 drop anchors through its subsampling map; the fused tail
+            # keeps every anchor of ONE stride-8 map, so it must not accept them
+            raise L.ShfError("ProposalLayer feat_stride %s: anchors on different strides are not on this path" % (lp["feat_stride"],))
         cls_blob, box_blob, info_blob = prop.bottoms
         chain = []
         r2 = by_top[cls_blob]                         # Reshape (0,2A,-1,0)
@@ -393,7 +422,10 @@ class GpuNet:
         dev = self.device
         Cf = heads[0][1].shape[1]
         t = lambda x: torch.from_numpy(np.ascontiguousarray(x, F32)).to(dev)
-        return dict(A=A, C=Cf, feats=[h[0] for h in heads], anchors=np.ascontiguousarray(anchors, F32),
+        shapes = spec.infer_shapes({})
+        if len({tuple(shapes[h[0]]) for h in heads}) != 1 or any(h[1].shape[1] != Cf for h in heads):
+            raise L.ShfError("detection tail: the head feature maps %s must share one shape" % [h[0] for h in heads])
+        return dict(A=A, C=Cf, name=prop.name, feats=[h[0] for h in heads], anchors=np.ascontiguousarray(anchors, F32),
                     wc=t(np.stack([h[1] for h in heads])), bc=t(np.stack([h[2] for h in heads])),
                     wb=t(np.stack([h[3] for h in heads])), bb=t(np.stack([h[4] for h in heads])),
                     stride=int(lp["feat_stride"][0]), tops=prop.tops, info=info_blob,
@@ -417,7 +449,41 @@ class GpuNet:
 
     def use_fast(self, im_scale) -> bool:
         """Operand-format policy for one pyramid level (see ``fast_min_scale``)."""
-        return self.fast_min_scale is not None and im_scale is not None and float(im_scale) >= self.fast_min_scale
+        return (self.fast_min_scale is not None and not self.fast_disabled and im_scale is not None
+                and float(im_scale) >= self.fast_min_scale)
+
+    # -- range guard ---------------------------------------------------------------------------------
+    def _gptr(self, fmt: int, slot: int):
+        return C.c_void_p(self.guard.data_ptr() + 4 * (fmt * self.guard.shape[1] + slot))
+
+    def range_report(self, guard: Optional[torch.Tensor] = None):
+        """[(layer, 'h2'|'hf8', max |x| written)] since the guard was last zeroed (synchronises)."""
+        g = (self.guard if guard is None else guard).cpu().numpy().view(np.float32)
+        out = []
+        for fmt, tag in ((FMT_H2, "h2"), (FMT_HF8, "hf8")):
+            for slot, (_, name) in enumerate(self.guard_ops):
+                if g[fmt, slot] != 0 or np.isnan(g[fmt, slot]):
+                    out.append((name, tag, float(g[fmt, slot])))
+        return out
+
+    def check_ranges(self, guard: Optional[torch.Tensor] = None) -> bool:
+        """Reads the range guard (a device->host copy: call at a point that synchronises anyway).  Raises RangeError when
+        any tensor left the fp16 range; returns True when a tensor written in the FAST format was outside the window its
+        fixed exponents cover (saturated ah8 bytes, or residual bytes short of their 4 bits) -- the caller must then
+        repeat those levels on split fp16 (``fast_disabled`` is set, so a plain re-run does that)."""
+        rep = self.range_report(guard)
+        bad = [(n, t, v) for n, t, v in rep if not (v < F16_MAX)]
+        if bad:
+            raise RangeError("activations outside the fp16 range of the operand formats: %s" %
+                             ", ".join("%s (%s) max |x| = %g" % b for b in bad))
+        trips = [(n, v) for n, t, v in rep if t == "hf8" and (v >= HF8_SATURATION or v < HF8_MIN_TENSOR_MAX)]
+        if trips and not self.fast_disabled:
+            import warnings
+            warnings.warn("smallhardface_b200: the fast f16+f8 operand format is outside its exponent window on this net "
+                          "(%s); switching this net to split-fp16 operands" %
+                          ", ".join("%s max |x| = %g" % t for t in trips[:4]), RuntimeWarning)
+            self.fast_disabled = True
+        return bool(trips)
 
     def forward(self, data: torch.Tensor, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False,
                 det_thresh=0.05):
@@ -450,7 +516,7 @@ class GpuNet:
                 n, _, h, w = x.shape
                 out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
                 L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
-                       s["scale"], int(s["relu"]), out.fmt, st)
+                       s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
             elif kind == "conv":
                 if x.c_off != 0 or x.c != x.ctot:
                     raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
@@ -469,10 +535,11 @@ class GpuNet:
                     L.call("shf_conv_igemm_pool", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t if out else None),
                            _ptr(pooled.t), x.n, x.h, x.w, s["cin"], s["cout"], s["k"], s["dil"],
                            out.ctot if out else s["cout"], out.c_off if out else 0, pooled.ctot, pooled.c_off,
-                           s["scale"], int(s["relu"]), x.fmt, pooled.fmt, st)
+                           s["scale"], int(s["relu"]), x.fmt, pooled.fmt, self._gptr(pooled.fmt, s["slot"]), st)
                 else:
                     L.call("shf_conv_igemm", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
-                           s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, st)
+                           s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt,
+                           self._gptr(out.fmt, s["slot"]), st)
                     if "pool_top" in s:                      # odd size: pooling could not be fused
                         if out.c_off != 0 or out.c != out.ctot:
                             raise L.ShfError("pool after %s reads a channel window; not supported" % l.name)
@@ -493,7 +560,7 @@ class GpuNet:
                 wo = s["s"] * (x.w - 1) + s["k"] - 2 * s["pad"]
                 out = self._alloc_out(l.tops[0], x.n, ho, wo, x.c, fmt)
                 L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
-                       s["pad"], out.ctot, out.c_off, x.fmt, out.fmt, st)
+                       s["pad"], out.ctot, out.c_off, x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
             self.launches += 1
 
     def run_tail(self, n_img, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False, det_thresh=0.05):

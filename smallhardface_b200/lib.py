@@ -18,6 +18,7 @@ _lib = None
 c_void_p, c_int, c_float, c_double, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
 
 FMT_H2, FMT_HF8 = 0, 1          # SHF_FMT_* of include/shf_b200.h
+ABI_VERSION = 3                 # shf_abi_version() of the library these signatures describe
 
 # name -> (restype, argtypes); must list every symbol include/shf_b200.h declares
 SIGNATURES = {
@@ -25,16 +26,17 @@ SIGNATURES = {
     "shf_abi_version": (c_int, []),
     "shf_device_info": (c_int, [c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_ll)]),
     "shf_conv_igemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+                               c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p]),
     "shf_conv_igemm_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                    c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+                                    c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p,
+                                    c_void_p]),
     "shf_set_conv_impl": (c_int, [c_int]),
     "shf_conv1_c3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_conv1_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
-                             c_void_p]),
+                             c_void_p, c_void_p]),
     "shf_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_deconv_depthwise": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_int, c_int, c_int, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "shf_h2_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_nchw_to_h2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_preprocess_level": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
@@ -98,6 +100,9 @@ def load():
             raise ShfError("libshf_b200.so does not export %s (stale build?)" % name)
         fn.restype = res
         fn.argtypes = args
+    if lib.shf_abi_version() != ABI_VERSION:
+        raise ShfError("%s is a stale build (ABI %d, this package needs %d): run `make -C %s`"
+                       % (LIB_PATH, lib.shf_abi_version(), ABI_VERSION, CSRC))
     _lib = lib
     return lib
 

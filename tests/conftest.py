@@ -24,7 +24,11 @@ def built_library():
     """The CUDA extension is git-ignored (it travels with the working tree): build it in-tree if a fresh checkout is
     being tested.  This only compiles; nothing here provides a substitute for the kernels."""
     from smallhardface_b200 import lib
-    if not os.path.exists(lib.LIB_PATH):
+    try:
+        if not os.path.exists(lib.LIB_PATH):
+            raise lib.ShfError("missing")
+        lib.load()                                   # raises on a stale ABI
+    except lib.ShfError:
         lib.build()
     return lib.LIB_PATH
 

@@ -87,7 +87,7 @@ def test_conv1_tensor_core_matches_oracle(H, W, fmt):
     packed, k = pack_conv1_weights(w)
     out = H2(torch.zeros((2, 2, H, W, 64), dtype=torch.float16, device=DEV), fmt=fmt)
     L.call("shf_conv1_tc", _ptr(dev(x)), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), 2, H, W, 64, float(2.0 ** -k), 1, fmt,
-           _stream())
+           None, _stream())
     got = out.to_nchw().cpu().numpy()
     ref = OL.relu(OL.conv(x, w, b, pad=(1, 1)))
     assert relerr(got, ref) < (2e-6 if fmt == 0 else 2 ** -14)
@@ -122,7 +122,7 @@ def test_conv_igemm_matches_oracle(cin, cout, H, W, k, dil, ctot, coff, relu):
     xin = H2.from_nchw(dev(x))
     out = H2(torch.zeros((2, 1, H, W, ctot), dtype=torch.float16, device=DEV), coff, cout)
     L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), 1, H, W, cin, cout, k, dil,
-           ctot, coff, float(2.0 ** -kexp), relu, 0, 0, _stream())
+           ctot, coff, float(2.0 ** -kexp), relu, 0, 0, None, _stream())
     torch.cuda.synchronize()
     got = out.to_nchw().cpu().numpy()
     pad = dil if k == 3 else 0
@@ -154,7 +154,7 @@ def test_conv_relu_pool_fused(cin, cout, H, W, write_full):
     full = H2.empty(2, H, W, cout, DEV) if write_full else None
     pooled = H2(torch.zeros((2, 2, H // 2, W // 2, cout + 64), dtype=torch.float16, device=DEV), 64, cout)
     L.call("shf_conv_igemm_pool", _ptr(xin.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(full.t if full else None),
-           _ptr(pooled.t), 2, H, W, cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, 0, 0, _stream())
+           _ptr(pooled.t), 2, H, W, cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, 0, 0, None, _stream())
     ref = OL.relu(OL.conv(x, w_eff, b, pad=(1, 1)))
     refp = OL.max_pool(ref)
     got = pooled.to_nchw().cpu().numpy()
@@ -173,7 +173,7 @@ def test_conv_igemm_batch2():
     xin = H2.from_nchw(dev(x))
     out = H2.empty(2, 18, 20, 64, DEV)
     L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed)), C.c_void_p(0), _ptr(out.t), 2, 18, 20, 64, 64, 3, 1, 64, 0,
-           float(2.0 ** -kexp), 0, 0, 0, _stream())
+           float(2.0 ** -kexp), 0, 0, 0, None, _stream())
     assert relerr(out.to_nchw().cpu().numpy(), OL.conv(x, w_eff, None, pad=(1, 1))) < 3e-6
 
 
@@ -193,7 +193,7 @@ def test_deconv_depthwise_into_concat_window():
     w = OL.bilinear_filler((c, 1, 4, 4)) * (1 + 0.1 * rng.rand(c, 1, 1, 1)).astype(F32)
     xin = H2.from_nchw(dev(x))
     dst = torch.zeros((2, 1, 2 * H, 2 * W, 512), dtype=torch.float16, device=DEV)
-    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(w)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 0, 0, 0, _stream())
+    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(w)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 0, 0, 0, None, _stream())
     got = H2(dst, 0, c).to_nchw().cpu().numpy()
     ref = OL.deconv(x, w, None, pad=(1, 1), stride=(2, 2), group=c)
     assert relerr(got, ref) < 1e-6
@@ -292,7 +292,7 @@ def test_conv_igemm_hf8_matches_operand_model(cin, cout, H, W, k, dil, ctot, cof
     L.call("shf_set_conv_impl", impl)
     try:
         L.call("shf_conv_igemm", _ptr(xin.t), _ptr(dev(packed8)), _ptr(dev(b)), _ptr(out.t), 1, H, W, cin, cout, k, dil,
-               ctot, coff, float(2.0 ** -kexp), relu, 1, ofmt, _stream())
+               ctot, coff, float(2.0 ** -kexp), relu, 1, ofmt, None, _stream())
         torch.cuda.synchronize()
     finally:
         L.call("shf_set_conv_impl", 8)
@@ -322,7 +322,7 @@ def test_conv_relu_pool_fused_hf8():
     full = H2.empty(2, H, W, cout, DEV, fmt=1)
     pooled = H2(torch.zeros((2, 2, H // 2, W // 2, cout + 64), dtype=torch.float16, device=DEV), 64, cout, fmt=1)
     L.call("shf_conv_igemm_pool", _ptr(xin.t), _ptr(dev(packed8)), _ptr(dev(b)), _ptr(full.t), _ptr(pooled.t), 2, H, W,
-           cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, 1, 1, _stream())
+           cin, cout, 3, 1, cout, 0, cout + 64, 64, float(2.0 ** -kexp), 1, 1, 1, None, _stream())
     assert relerr(full.to_nchw().cpu().numpy(), model) < 2 ** -13
     assert relerr(pooled.to_nchw().cpu().numpy(), OL.max_pool(model)) < 2 ** -13
     assert torch.all(pooled.t[0][..., :64] == 0)
@@ -347,7 +347,7 @@ def test_simt_layers_hf8():
     wd = OL.bilinear_filler((c, 1, 4, 4)) * (1 + 0.1 * rng.rand(c, 1, 1, 1)).astype(F32)
     xin = H2.from_nchw(dev(xd), fmt=1)
     dst = torch.zeros((2, 1, 2 * H, 2 * W, 512), dtype=torch.float16, device=DEV)
-    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(wd)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 256, 1, 1, _stream())
+    L.call("shf_deconv_depthwise", _ptr(xin.t), _ptr(dev(wd)), _ptr(dst), 1, H, W, c, 4, 2, 1, 512, 256, 1, 1, None, _stream())
     got = H2(dst, 256, c, fmt=1).to_nchw().cpu().numpy()
     assert relerr(got, OL.deconv(xd, wd, None, pad=(1, 1), stride=(2, 2), group=c)) < 2 ** -14
     assert torch.all(dst[0][..., :256] == 0)

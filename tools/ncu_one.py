@@ -14,5 +14,5 @@ w = (np.random.RandomState(0).randn(cout, cin, k, k) * 0.02).astype(np.float32)
 packed, kexp = (pack_conv_weights_hf8 if fmt else pack_conv_weights)(w)
 wd = torch.from_numpy(packed).to(dev); bd = torch.zeros(cout, device=dev); out = H2.empty(1, H, W, cout, dev, fmt)
 for _ in range(3):
-    L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0, float(2.0 ** -kexp), 1, fmt, fmt, _stream())
+    L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0, float(2.0 ** -kexp), 1, fmt, fmt, None, _stream())
 torch.cuda.synchronize()

@@ -22,10 +22,10 @@ for name, cin, cout, H, W in SHAPES:
                 os.environ["SHF_PROBE_EPI"] = str(probe)
                 if pool:
                     run = lambda: L.call("shf_conv_igemm_pool", _ptr(xs[fmt].t), _ptr(wd[fmt]), _ptr(b), None, _ptr(pooled.t), 1, H, W,
-                                         cin, cout, 3, 1, cout, 0, cout, 0, float(2.0 ** -kexp), 1, fmt, fmt, _stream())
+                                         cin, cout, 3, 1, cout, 0, cout, 0, float(2.0 ** -kexp), 1, fmt, fmt, None, _stream())
                 else:
                     run = lambda: L.call("shf_conv_igemm", _ptr(xs[fmt].t), _ptr(wd[fmt]), _ptr(b), _ptr(out.t), 1, H, W, cin, cout, 3,
-                                         1, cout, 0, float(2.0 ** -kexp), 1, fmt, fmt, _stream())
+                                         1, cout, 0, float(2.0 ** -kexp), 1, fmt, fmt, None, _stream())
                 run(); torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

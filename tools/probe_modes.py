@@ -21,7 +21,7 @@ for name, cin, cout, H, W, k, dil in SHAPES:
     for impl, mode in ((7, 0), (8, 0), (7, 1), (8, 1)):
         L.call("shf_set_conv_impl", impl)
         run = lambda: L.call("shf_conv_igemm", _ptr(xs[mode].t), _ptr(wd[mode]), _ptr(b), _ptr(out.t), 1, H, W, cin, cout, k,
-                             dil, cout, 0, float(2.0 ** -kexp), 1, mode, mode, _stream())
+                             dil, cout, 0, float(2.0 ** -kexp), 1, mode, mode, None, _stream())
         run(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

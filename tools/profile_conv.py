@@ -31,7 +31,7 @@ for name, cin, cout, H, W, k, dil in SHAPES:
     out = H2.empty(1, H, W, cout, dev)
     def run():
         L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(b), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0,
-               float(2.0 ** -kexp), 1, 0, 0, _stream())
+               float(2.0 ** -kexp), 1, 0, 0, None, _stream())
     run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -9,7 +9,7 @@ L.call("shf_set_conv_impl", impl)
 x = H2(torch.randn((2, 1, H, W, cin), device=dev).abs().half())
 packed, kexp = pack_conv_weights((np.random.RandomState(0).randn(cout, cin, k, k) * 0.02).astype(np.float32))
 wd = torch.from_numpy(packed).to(dev); bd = torch.zeros(cout, device=dev); out = H2.empty(1, H, W, cout, dev)
-run = lambda: L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0, float(2.0 ** -kexp), 1, 0, 0, _stream())
+run = lambda: L.call("shf_conv_igemm", _ptr(x.t), _ptr(wd), _ptr(bd), _ptr(out.t), 1, H, W, cin, cout, k, dil, cout, 0, float(2.0 ** -kexp), 1, 0, 0, None, _stream())
 for _ in range(2): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
