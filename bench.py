@@ -307,7 +307,7 @@ def run_ours(args):
         b = det.detect_device(dev_imgs)
         if world > 1:
             # the one collective: all-gather of boxes, queued behind the box voting on its side stream
-            det.run_after_results(b, lambda: gather_detections(b["out_dets"], b["out_count"], world))
+            det.run_after_results(b, lambda: gather_detections(b["out_dets"], b["out_count"], world, det.cfg.gather_rows))
         return b
 
     def step_e2e():

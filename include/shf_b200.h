@@ -110,7 +110,8 @@ int shf_preprocess_level_batched(const uint8_t* imgs_nhwc, int num_images, int h
  * w_cls [A][2][C], b_cls [A][2], w_box [A][4][C], b_box [A][4], all fp32 [dev]; base_anchors: host [A][4].
  * Outputs [dev]: prob (2A,H,W) fp32 = cls_prob_reshape_output; delta (4A,H,W) = bbox_pred_output;
  * boxes (H*W*A,4) decoded+clipped, rows ordered (h,w,a); keys (H*W*A) u64 sort keys
- * ((~score_bits)<<32 | row, ~0 for rows below score_thresh / min_size); count = rows >= score_thresh;
+ * (desc(score)<<32 | row with desc() = complement of the order-preserving integer image of a float, so ascending keys =
+ * descending scores for any float; ~0 for rows below score_thresh / min_size); count = rows >= score_thresh;
  * best_key = smallest key over rows passing min_size. */
 int shf_head_decode(const void* const* feat_h2, long long feat_plane_stride, int num_anchors, const float* w_cls,
                     const float* b_cls, const float* w_box, const float* b_box, const float* base_anchors, int H, int W,
@@ -120,7 +121,7 @@ int shf_head_decode(const void* const* feat_h2, long long feat_plane_stride, int
 
 /* The same for all images of one pyramid-level batch in ONE launch (the pyramid driver's form).  feat_h2 point at
  * image 0; image i starts feat_image_stride elements later.  Outputs are [image][...] slices of the single-image
- * layout; keys are tagged [image:5][~score:32][row:27] so one shf_sort_keys over num_images*n keys sorts every image. */
+ * layout; keys are tagged [image:5][desc(score):32][row:27]; shf_sort_keys with one segment per image slot orders them. */
 int shf_head_decode_batched(const void* const* feat_h2, long long feat_plane_stride, long long feat_image_stride,
                             int num_images, int num_anchors, const float* w_cls, const float* b_cls, const float* w_box,
                             const float* b_box, const float* base_anchors, int H, int W, int C, int feat_stride,
@@ -136,13 +137,18 @@ int shf_gather_dets_batched(const unsigned long long* sorted_keys, const int* co
                             int passes_per_image, float* dets, int* pass_offsets, int image_base, int passes_total,
                             int pass_base, int det_cap, float level_w, float im_scale, float det_thresh, void* stream);
 
-/* `max_score.argsort()[::-1]` (proposal_layer.py:181) as an ascending, STABLE radix sort of the keys above
- * (ties: lower row first).  begin_bit: lowest key bit that takes part; when the keys arrive in ascending order of
- * their row field (as shf_head_decode* writes them) pass the width of that field (32, or 27 for the batched keys) and
- * stability orders the ties -- 0 sorts all 64 bits. */
-long long shf_sort_keys_workspace(int n);
-int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int n, int begin_bit, void* workspace,
-                  long long workspace_bytes, void* stream);
+/* `max_score.argsort()[::-1]` (proposal_layer.py:181; also lib/test.py:182, cpu_nms.pyx:25) as an ascending, STABLE,
+ * segmented radix sort of the keys above, hand-written (one CTA per segment, one launch): segment s occupies
+ * keys[s * segment_stride, + len), len = min(segment_len[s], fixed_len) (segment_len [dev] may be NULL: fixed_len).
+ * Keys whose 32-bit score field (bits [begin_bit, begin_bit + 32)) is all ones are sentinels ("not a candidate") and
+ * are dropped; the survivors are ordered by that field alone and ties keep their arrival order -- the keys arrive in
+ * ascending row order, so ties resolve to the lower row, the order the oracle defines.  begin_bit = 32 for
+ * shf_head_decode keys, 27 for the image-tagged batched keys (segment = image slot).  keys_out[s * stride, + survivors)
+ * holds the result (the rest of the segment is ~0); keys_in is left untouched.  workspace: one more key buffer. */
+long long shf_sort_keys_workspace(int total_keys);
+int shf_sort_keys(const unsigned long long* keys_in, unsigned long long* keys_out, int num_segments, int segment_stride,
+                  const int* segment_len, int fixed_len, int begin_bit, void* workspace, long long workspace_bytes,
+                  void* stream);
 
 /* proposal_layer.py:183-220: R = min(count, topn) rows (1 if nothing cleared the threshold) ->
  * out_boxes (topn,5) [0,x1,y1,x2,y2], out_probs (topn,2) [bg,fg], *out_rows = R  [all dev].
@@ -159,7 +165,10 @@ int shf_proposal_gather(const unsigned long long* sorted_keys, const int* count,
  *             (lib/nms/cpu_nms.pyx:17-68 for mode 0 `(double)ovr >= thresh`; lib/nms/nms_kernel.cu:45-155 for
  *              mode 1 `ovr > (float)thresh`; mode 2 `ovr >= (float)thresh`)
  *   method 1: bbox_vote (lib/test.py:181-217) -> out_dets[i][out_cap][5], singleton clusters dropped.
- * out_count[i] = rows produced.  cap_per_image bounds rows considered per image. */
+ * out_count[i] = rows PRODUCED, which may exceed out_cap: only the first out_cap are stored and the caller must treat
+ * out_count[i] > out_cap as an error (box voting cannot produce more than cap_per_image / 2 + 1 rows, NMS no more than
+ * cap_per_image).  cap_per_image bounds rows considered per image.  Images with up to 16384 rows use IoU bit masks
+ * (parallel 64 x 64 tiles + a 64-rows-per-step sweep), larger ones a serial one-CTA sweep; same results. */
 long long shf_postprocess_workspace(int num_images, int cap_per_image);
 int shf_postprocess(const float* dets, const int* seg_begin, const int* seg_end, int num_images, int cap_per_image,
                     double thresh, int method, int mode, int* out_idx, float* out_dets, int* out_count, int out_cap,

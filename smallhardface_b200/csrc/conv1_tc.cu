@@ -191,13 +191,13 @@ extern "C" int shf_conv1_tc(const float* in_nchw, const void* w_packed, const fl
   p.out_scale = out_scale;
   p.guard = range_guard;
   const int smem_bytes = 1024 + 49152 + 16 + 256;
-  static bool attr = false;
-  if (!attr) {
-    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  static bool attr[64] = {};                     // function attributes are per device
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (dev >= 0 && dev < 64) attr[dev] = true;
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int max_grid = sms * 4;                  // four resident CTAs per SM overlap gather, MMA and store phases
   const int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;

@@ -403,10 +403,12 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 template <int BN, int CTAS>
 int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
                   cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};                   // function attributes are per device
+  int dev = 0;
+  SHF_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
     SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   if (CTAS == 1) {
     conv_stream_kernel<BN, CTAS><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
@@ -430,12 +432,14 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamPara
 }
 
 int sm_count() {
-  static int n = 0;
+  static int cached[64] = {};                  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = (dev >= 0 && dev < 64) ? cached[dev] : 0;
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
   }
   return n;
 }

@@ -39,7 +39,9 @@ class DetectConfig:
     max_resolution: int = 16                                   # MAX_RESOLUTION
     pixel_means: Sequence[float] = (102.9801, 115.9465, 122.7717)   # PIXEL_MEANS
     nms_mode: int = 0                                          # 0 = cpu_nms (>=), 1 = gpu_nms (>)
-    max_dets_out: int = 4096                                   # rows returned per image (post vote / NMS)
+    # rows of the device result buffers are sized from the input (cap / 2 + 1 for voting, cap for NMS: nothing can be
+    # truncated); ``gather_rows`` only sizes the multi-GPU all-gather payload, and exceeding it raises (parallel.py)
+    gather_rows: int = 4096
     # not a reference key: pyramid levels with im_scale >= this run the convs on the fast f16+f8 operand format, smaller
     # (error-magnifying) levels on precise split fp16; None = precise everywhere (see GpuNet / tools/precision_model.py)
     fast_min_scale: float | None = 0.9
@@ -82,6 +84,7 @@ class Detector:
                           fast_min_scale=self.cfg.fast_min_scale)
         self._means = (C.c_double * 3)(*self.cfg.pixel_means)
         self._bufs = {}
+        self._staging = {}                   # (slot, shape) -> [pinned tensor, event of its last upload]
         self._flip = 0
         self._post_stream = None             # box voting / NMS of call i overlaps the conv stack of call i+1
         self.max_batch_bytes = 40e9          # activation budget used to size per-level batches (180 GB HBM per GPU)
@@ -90,11 +93,21 @@ class Detector:
     def upload(self, images: List[np.ndarray]) -> List[torch.Tensor]:
         """uint8 HWC BGR host images -> device tensors (through pinned staging, async on the current stream)."""
         out = []
-        for im in images:
+        for i, im in enumerate(images):
             if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
                 raise ValueError("images must be uint8 HxWx3 (cv2.imread layout)")
-            pin = torch.from_numpy(np.ascontiguousarray(im)).pin_memory()
-            out.append(pin.to(self.device, non_blocking=True))
+            key = (i, im.shape)
+            st = self._staging.get(key)
+            if st is None:                   # page-locked staging is allocated once per (slot, shape) and reused
+                if len(self._staging) >= 256:
+                    self._staging.clear()
+                st = self._staging[key] = [torch.empty(im.shape, dtype=torch.uint8, pin_memory=True), None]
+            if st[1] is not None:
+                st[1].synchronize()          # the previous upload from this buffer has been consumed
+            st[0].numpy()[...] = im
+            out.append(st[0].to(self.device, non_blocking=True))
+            st[1] = torch.cuda.Event()
+            st[1].record()
         return out
 
     def _buffers(self, batch: int, passes: int):
@@ -107,12 +120,15 @@ class Detector:
             cap = passes * self.net.cfg["pre_nms_topn"]
             dev = self.device
             ws_bytes = int(L.load().shf_postprocess_workspace(batch, cap))
-            b = dict(cap=cap, dets=torch.empty((batch, cap, 5), dtype=torch.float32, device=dev),
+            # voting emits at most one row per cluster of >= 2 members plus one last singleton; NMS at most every row
+            out_cap = cap // 2 + 1 if self.cfg.nms_method == "BBOX_VOTE" else cap
+            b = dict(cap=cap, out_cap=out_cap, guard=torch.zeros_like(self.net.guard),
+                     dets=torch.empty((batch, cap, 5), dtype=torch.float32, device=dev),
                      offs=torch.zeros((batch, passes + 1), dtype=torch.int32, device=dev),
                      seg_begin=(torch.arange(batch, dtype=torch.int32, device=dev) * cap).contiguous(),
                      seg_end=torch.empty((batch,), dtype=torch.int32, device=dev),
-                     out_dets=torch.empty((batch, self.cfg.max_dets_out, 5), dtype=torch.float32, device=dev),
-                     out_idx=torch.empty((batch, self.cfg.max_dets_out), dtype=torch.int32, device=dev),
+                     out_dets=torch.empty((batch, out_cap, 5), dtype=torch.float32, device=dev),
+                     out_idx=torch.empty((batch, out_cap), dtype=torch.int32, device=dev),
                      out_count=torch.zeros((batch,), dtype=torch.int32, device=dev),
                      ws=torch.empty((ws_bytes,), dtype=torch.uint8, device=dev), ws_bytes=ws_bytes)
             self._bufs[key] = b
@@ -149,6 +165,9 @@ class Detector:
         if b.get("done") is not None:
             torch.cuda.current_stream().wait_event(b["done"])      # this set's previous post-processing has finished
         b["offs"].zero_()
+        b["guard"].zero_()
+        self.net.guard = b["guard"]          # this call's range-guard slots (read back in download())
+        b["images"] = dev_images
         groups = {}
         for i, img in enumerate(dev_images):
             groups.setdefault((img.shape[0], img.shape[1]), []).append(i)
@@ -186,11 +205,11 @@ class Detector:
             torch.add(b["seg_begin"], b["offs"][:, passes], out=b["seg_end"])
             L.call("shf_postprocess", _ptr(b["dets"]), _ptr(b["seg_begin"]), _ptr(b["seg_end"]), B, b["cap"],
                    float(cfg.nms_thresh), method, int(cfg.nms_mode), _ptr(b["out_idx"]), _ptr(b["out_dets"]),
-                   _ptr(b["out_count"]), cfg.max_dets_out, _ptr(b["ws"]), b["ws_bytes"], _stream())
+                   _ptr(b["out_count"]), b["out_cap"], _ptr(b["ws"]), b["ws_bytes"], _stream())
             done = torch.cuda.Event()
             done.record()
         b["done"] = done
-        self.net.launches += 3 + B
+        self.net.launches += 7               # seg_end add + det_keys, sort, sorted boxes, IoU masks, sweep, reduce / emit
         return b
 
     def run_after_results(self, b, fn):
@@ -214,9 +233,18 @@ class Detector:
         ``bbox_vote`` returns; float32 rows of ``dets`` for NMS)."""
         self.wait_results(b)
         counts = b["out_count"][:B].cpu().numpy()
+        # the range guard rides on the synchronisation the counts just paid for; a fast-format level outside its
+        # exponent window disables the format (sticky) and the call is repeated on split fp16
+        if self.net.check_ranges(b["guard"]) and b.get("images") is not None and not b.get("retried"):
+            b2 = self.detect_device(b["images"])
+            b2["retried"] = True
+            return self.download(b2, B)
+        if int(counts.max(initial=0)) > b["out_cap"]:
+            raise L.ShfError("post-processing produced %d rows for one image but the buffer holds %d"
+                             % (int(counts.max()), b["out_cap"]))
         slots = []
         if self.cfg.nms_method == "BBOX_VOTE":
-            host = b["out_dets"][:B].cpu().numpy()
+            host = b["out_dets"][:B, :max(1, int(counts.max(initial=0)))].cpu().numpy()
             for k in range(B):
                 slots.append(host[k, :counts[k]].astype(np.float64))
         else:

@@ -502,8 +502,7 @@ class GpuNet:
         if fast and self.fast_min_scale is None:
             raise L.ShfError("this GpuNet was built without the fast operand format (fast_min_scale=None)")
         fmt = FMT_HF8 if fast else FMT_H2
-        T = self.tensors
-        T.clear()
+        T = self.tensors = OrderedDict()          # a fresh table: a captured graph keeps the one it was recorded with
         T["data"] = data
         st = _stream()
         for kind, l, s in self.ops:
@@ -575,45 +574,93 @@ class GpuNet:
             raise L.ShfError("image index %d outside the batch of %d" % (n_img, f0.n))
         H, W = f0.h, f0.w
         hw, n = H * W, H * W * A
-        key = ("tailbuf", n)
-        buf = getattr(self, "_tailbuf", None)
-        if buf is None or buf["n"] != n:
+        bufs = self.__dict__.setdefault("_tailbufs", {})
+        buf = bufs.get(n)                  # never freed or replaced: captured CUDA graphs hold these addresses
+        if buf is None:
             ws_bytes = int(L.load().shf_sort_keys_workspace(n))
             topn = self.cfg["pre_nms_topn"] if self.cfg["pre_nms_topn"] > 0 else n
+            topn = min(topn, n)
+            # one contiguous result block: [rows (int32) + 3 pad | boxes (topn, 5) | probs (topn, 2)] -> ONE device->host copy
+            pack = torch.zeros((4 + 7 * topn,), dtype=torch.float32, device=dev)
             buf = dict(n=n, prob=torch.empty((2 * A, H, W), dtype=torch.float32, device=dev),
                        delta=torch.empty((4 * A, H, W), dtype=torch.float32, device=dev),
                        boxes=torch.empty((n, 4), dtype=torch.float32, device=dev),
                        keys=torch.empty((n,), dtype=torch.int64, device=dev),
                        skeys=torch.empty((n,), dtype=torch.int64, device=dev),
-                       meta=torch.zeros((4,), dtype=torch.int64, device=dev),      # [count|rows], best_key
+                       meta=torch.zeros((4,), dtype=torch.int64, device=dev),      # count, (unused), best_key
                        ws=torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev), ws_bytes=ws_bytes,
-                       out_boxes=torch.empty((min(topn, n), 5), dtype=torch.float32, device=dev),
-                       out_probs=torch.empty((min(topn, n), 2), dtype=torch.float32, device=dev), topn=min(topn, n))
-            self._tailbuf = buf
+                       pack=pack, out_boxes=pack[4:4 + 5 * topn].view(topn, 5),
+                       out_probs=pack[4 + 5 * topn:].view(topn, 2), topn=topn)
+            bufs[n] = buf
         st = _stream()
         img_bytes = H * W * Cf * 2
         fp = (C.c_void_p * A)(*[f.t.data_ptr() + n_img * img_bytes for f in feats])
         plane_stride = f0.n * H * W * Cf
         anchors = t["anchors"]
         ap = anchors.ctypes.data_as(C.POINTER(C.c_float))
-        meta32 = buf["meta"].view(torch.int32)
         count_ptr = C.c_void_p(buf["meta"].data_ptr())
-        rows_ptr = C.c_void_p(buf["meta"].data_ptr() + 4)
+        rows_ptr = C.c_void_p(buf["pack"].data_ptr())
         best_ptr = C.c_void_p(buf["meta"].data_ptr() + 8)
         im_h, im_w, im_scale = float(im_info[0]), float(im_info[1]), float(im_info[2])
         min_size = float(F32(self.cfg["min_size"]) * F32(im_scale))
         L.call("shf_head_decode", fp, plane_stride, A, _ptr(t["wc"]), _ptr(t["bc"]), _ptr(t["wb"]), _ptr(t["bb"]), ap, H, W, Cf,
                t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])), _ptr(buf["prob"]), _ptr(buf["delta"]),
                _ptr(buf["boxes"]), _ptr(buf["keys"]), count_ptr, best_ptr, st)
-        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), n, 32, _ptr(buf["ws"]), buf["ws_bytes"], st)
+        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), 1, n, None, n, 32, _ptr(buf["ws"]), buf["ws_bytes"], st)
         L.call("shf_proposal_gather", _ptr(buf["skeys"]), count_ptr, best_ptr, _ptr(buf["prob"]), _ptr(buf["boxes"]), A,
                hw, buf["topn"], _ptr(buf["out_boxes"]), _ptr(buf["out_probs"]), rows_ptr,
                _ptr(dets), _ptr(pass_offsets), int(pass_idx), int(det_cap), int(bool(flip)), float(F32(im_w)),
                float(F32(im_scale)), float(F32(det_thresh)), st)
-        self.launches += 5       # memset x2 inside head_decode are not kernels; decode + sort (>=2) + gather
+        self.launches += 3       # memset x2 inside head_decode are not kernels; decode + sort + gather
         T[t["cls_blob"]] = buf["prob"].view(1, 2 * A, H, W)
         T[t["box_blob"]] = buf["delta"].view(1, 4 * A, H, W)
-        return buf["out_boxes"], buf["out_probs"], meta32[1:2]
+        self.last_pack = buf["pack"]
+        return buf["out_boxes"], buf["out_probs"], buf["pack"][:1].view(torch.int32)
+
+    # -- plugin path: one CUDA graph per (padded shape, im_info, operand format) ------------------------------
+    def forward_cached(self, data_src: torch.Tensor, im_info):
+        """``forward`` for the batch-1 plugin surface: ``data_src`` is the (1,3,H,W) float32 level blob in PAGE-LOCKED host
+        memory (or on the device).  The whole forward -- ~25 launches whose arguments depend only on the padded shape,
+        ``im_info`` and the operand format -- is captured once into a CUDA graph with its activations in the graph's own
+        memory pool and replayed afterwards: one upload + one graph launch per forward instead of a ctypes call and two
+        tensor-map encodes per layer.  Returns the device result block ``pack`` (see run_tail) or None (no tail).
+        Graphs live in an LRU bounded by ``graph_budget_bytes`` / ``graph_max_entries``."""
+        import os
+        info = (float(im_info[0]), float(im_info[1]), float(im_info[2]))
+        fast = self.use_fast(info[2])
+        key = (tuple(data_src.shape), info, fast, tuple(sorted(self.cfg.items())))
+        cache = self.__dict__.setdefault("_graphs", OrderedDict())
+        ent = cache.get(key)
+        if ent is None:
+            x = torch.empty(tuple(data_src.shape), dtype=torch.float32, device=self.device)
+            x.copy_(data_src, non_blocking=True)
+            if os.environ.get("SHF_CUDA_GRAPHS", "1") == "0" or self.profile:
+                res = self.forward(x, info)
+                return None if res is None else self.last_pack
+            # eager warm-up (function attributes, the persistent tail buffers), then the capture
+            l0 = self.launches
+            self.forward(x, info)
+            n_launch = self.launches - l0
+            torch.cuda.current_stream().synchronize()
+            before = torch.cuda.memory_allocated(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self.forward(x, info)
+            self.launches -= n_launch                         # the capture pass launched nothing
+            ent = dict(graph=g, x=x, pack=None if res is None else self.last_pack, tensors=self.tensors, launches=n_launch,
+                       bytes=max(0, torch.cuda.memory_allocated(self.device) - before) + x.numel() * 4)
+            cache[key] = ent
+            budget = getattr(self, "graph_budget_bytes", 48e9)
+            while len(cache) > 1 and (len(cache) > getattr(self, "graph_max_entries", 64)
+                                      or sum(e["bytes"] for e in cache.values()) > budget):
+                cache.popitem(last=False)                     # least recently used: frees its pool
+        else:
+            cache.move_to_end(key)
+            ent["x"].copy_(data_src, non_blocking=True)
+        ent["graph"].replay()
+        self.tensors = ent["tensors"]
+        self.launches += ent["launches"]
+        return ent["pack"]
 
     def run_tail_batched(self, nf, im_info, dets, pass_offsets, image_base, passes_total, pass_base, det_cap,
                          det_thresh=0.05):
@@ -655,12 +702,12 @@ class GpuNet:
                _ptr(t["bb"]), ap, H, W, Cf, t["stride"], im_h, im_w, min_size, float(F32(self.cfg["score_thresh"])),
                _ptr(buf["prob"]), _ptr(buf["delta"]), _ptr(buf["boxes"]), _ptr(buf["keys"]), _ptr(buf["count"]),
                _ptr(buf["best"]), st)
-        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), N * n, 27, _ptr(buf["ws"]), buf["ws_bytes"], st)
+        L.call("shf_sort_keys", _ptr(buf["keys"]), _ptr(buf["skeys"]), N, n, None, n, 27, _ptr(buf["ws"]), buf["ws_bytes"], st)
         L.call("shf_gather_dets_batched", _ptr(buf["skeys"]), _ptr(buf["count"]), _ptr(buf["best"]), _ptr(buf["prob"]),
                _ptr(buf["boxes"]), A, hw, min(topn, n), N // nf, nf, _ptr(dets), _ptr(pass_offsets), int(image_base),
                int(passes_total), int(pass_base), int(det_cap), float(F32(im_w)), float(F32(im_scale)),
                float(F32(det_thresh)), st)
-        self.launches += 7
+        self.launches += 3
 
     # -- blob access ---------------------------------------------------------------------------------------
     def blob_nchw(self, name: str) -> torch.Tensor:

@@ -53,7 +53,7 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                         c_void_p]),
     "shf_sort_keys_workspace": (c_ll, [c_int]),
-    "shf_sort_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "shf_sort_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "shf_proposal_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                     c_float, c_void_p]),

@@ -21,24 +21,40 @@ def shard_range(n_images: int, world: int, rank: int) -> Tuple[int, int]:
     return min(per * rank, n_images), min(per * (rank + 1), n_images)
 
 
-def gather_detections(out_dets: torch.Tensor, out_count: torch.Tensor, world: int):
-    """all_gather of (B, cap, 5) boxes and (B,) counts -> lists ordered by rank (device tensors)."""
+def gather_detections(out_dets: torch.Tensor, out_count: torch.Tensor, world: int, rows: int = 4096):
+    """The path's ONE collective: every rank contributes a (B, rows + 1, 5) float32 block -- row 0 of each image carries
+    its detection count (int32 bits in column 0), rows 1.. the first ``rows`` boxes -- and receives everybody's
+    (replaces the mp.Queue pickling of ``lib/test.py:336-344``).  Returns the gathered (world, B, rows + 1, 5) tensor;
+    ``merge_gathered`` unpacks it and RAISES if an image had more than ``rows`` detections (nothing is cut silently)."""
+    B = out_dets.shape[0]
+    rows = min(rows, out_dets.shape[1])
+    pack = torch.empty((B, rows + 1, 5), dtype=torch.float32, device=out_dets.device)
+    pack[:, 1:, :] = out_dets[:, :rows, :]
+    pack[:, 0, :] = 0.0
+    pack[:, 0, 0] = out_count.to(torch.int32).view(torch.float32)
     if world == 1:
-        return [out_dets], [out_count]
-    dets = [torch.empty_like(out_dets) for _ in range(world)]
-    cnts = [torch.empty_like(out_count) for _ in range(world)]
-    dist.all_gather(dets, out_dets.contiguous())
-    dist.all_gather(cnts, out_count.contiguous())
-    return dets, cnts
+        return pack.unsqueeze(0)
+    out = torch.empty((world,) + tuple(pack.shape), dtype=torch.float32, device=pack.device)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(out, pack)               # ncclAllGather straight into the result tensor
+    else:
+        dist.all_gather(list(out.unbind(0)), pack)           # gloo (CPU tests)
+    return out
 
 
-def merge_gathered(dets: List[torch.Tensor], cnts: List[torch.Tensor], n_images: int, world: int) -> List[np.ndarray]:
+def merge_gathered(gathered: torch.Tensor, n_images: int, world: int) -> List[np.ndarray]:
     """Rank-ordered concatenation, trimmed to each rank's real shard size (``lib/test.py:342-344``)."""
+    g = gathered.cpu()
+    counts = g[:, :, 0, 0].contiguous().view(torch.int32).numpy()
+    g = g.numpy()
+    rows = g.shape[2] - 1
     out: List[np.ndarray] = []
     for r in range(world):
         a, b = shard_range(n_images, world, r)
-        d = dets[r].cpu().numpy()
-        c = cnts[r].cpu().numpy()
         for i in range(b - a):
-            out.append(d[i, :int(c[i])].copy())
+            c = int(counts[r, i])
+            if c > rows:
+                raise RuntimeError("image %d of rank %d has %d detections, the gather payload carries %d rows: raise "
+                                   "gather_rows" % (i, r, c, rows))
+            out.append(g[r, i, 1:1 + c].copy())
     return out

@@ -13,8 +13,9 @@ if not torch.cuda.is_available():
 from oracle import detect as OD
 from oracle import postprocess as OP
 from oracle import preprocess as OPRE
-from oracle.net import OracleNet
+from oracle.indep_net import IndepNet
 from smallhardface_b200 import compat, deploy
+from test_gpu_net import match_rows
 
 compat.install()
 import caffe                                    # noqa: E402  (our drop-in)
@@ -71,22 +72,23 @@ def test_net_surface_and_forward_like_lib_test(deployed):
     with pytest.raises(RuntimeError, match="Could not open file"):
         caffe.Net("/nonexistent.prototxt", str(model), caffe.TEST)
 
-    onet = OracleNet(proto, model, engine="sgemm", fast=True)
+    onet = IndepNet(proto, model, engine="sgemm")
     im = deploy.synthetic_image(7, (90, 140))
     scales = OPRE.pyramid_scales(im.shape, (300, 600))
     blobs = OPRE.get_image_blobs(im, scales)
+    worst = 0.0
     for blob, s in zip(blobs, scales):
         for flip in (False, True):
             d = np.ascontiguousarray(blob[..., ::-1]) if flip else blob
             probs, boxes = forward_net_like_reference(net, {"data": d}, s, flip)
             rp, rb = OD.forward_level(onet, d, s, flip)
-            # a score within float noise of SCORE_THRESH may fall on either side of it
-            assert abs(len(probs) - len(rp)) <= max(2, len(rp) // 500) and boxes.shape[0] == probs.shape[0]
-            n = min(len(probs), len(rp))
-            # same row order unless two scores are within float noise of each other: compare sorted-by-score sets
-            assert np.abs(np.sort(probs[:, 1])[::-1][:n] - np.sort(rp[:, 1])[::-1][:n]).max() < 1e-3
-            k = min(50, n)
-            assert np.abs(boxes[:k, :4] - rb[:k]).max() < 1e-2 or np.abs(np.sort(boxes[:k, 0]) - np.sort(rb[:k, 0])).max() < 1e-2
+            # every reference row has a device row within 1e-3 (score) / 1e-2 raw px (box); rank swaps between
+            # near-equal scores and rows straddling SCORE_THRESH are the only freedoms (match_rows)
+            assert boxes.shape[0] == probs.shape[0]
+            ws, wb = match_rows(boxes[:, :4], probs[:, 1], rb[:, :4], rp[:, 1])
+            assert ws < 1e-3 and wb < 1e-2, (s, flip, ws, wb)
+            worst = max(worst, wb)
+    print("plugin surface: worst box error %.2e raw px" % worst)
     # views alias blob storage: an in-place edit is visible through net.blobs (what the flip fix relies on)
     out = net.forward(data=net.blobs["data"].data.copy(), im_info=net.blobs["im_info"].data.copy())
     out["boxes"][:, 1] = -7

@@ -395,10 +395,11 @@ def _run_tail(feat_nchw, wc, bc, wb, bb, im_info, topn=10000, score_thresh=0.002
     L.call("shf_head_decode", fp, 0, A, _ptr(dev(wc)), _ptr(dev(bc)), _ptr(dev(wb)), _ptr(dev(bb)),
            anchors.ctypes.data_as(C.POINTER(C.c_float)), H, W, Cc, 8, float(im_info[0]), float(im_info[1]), 0.0,
            float(F32(score_thresh)), _ptr(prob), _ptr(delta), _ptr(boxes), _ptr(keys), cptr, bptr, _stream())
-    L.call("shf_sort_keys", _ptr(keys), _ptr(skeys), n, 32, _ptr(ws), ws_bytes, _stream())     # stable: ties keep row order
-    full = torch.empty_like(skeys)
-    L.call("shf_sort_keys", _ptr(keys), _ptr(full), n, 0, _ptr(ws), ws_bytes, _stream())
-    assert torch.equal(full, skeys), "score-bits-only stable sort must equal the full 64-bit sort"
+    L.call("shf_sort_keys", _ptr(keys), _ptr(skeys), 1, n, None, n, 32, _ptr(ws), ws_bytes, _stream())   # stable: ties keep row order
+    valid = keys[keys != -1]                                     # sentinels (~0) are dropped by the sort
+    assert torch.equal(skeys[:valid.numel()], torch.sort(valid).values), \
+        "stable sort of the score field must equal a full 64-bit sort of (desc score, row) keys"
+    assert bool((skeys[valid.numel():] == -1).all())
     L.call("shf_proposal_gather", _ptr(skeys), cptr, bptr, _ptr(prob), _ptr(boxes), A, H * W, min(topn, n), _ptr(ob),
            _ptr(op), rptr, C.c_void_p(0), C.c_void_p(0), 0, 0, 0, 0.0, 1.0, 0.05, _stream())
     R = int(meta.view(torch.int32)[1].item())
@@ -450,9 +451,10 @@ def test_sort_ties_lower_index_first():
     assert np.array_equal(boxes, ref_boxes) and np.array_equal(probs, ref_probs)
 
 
-def _postprocess(dets_list, method, thresh=0.4, mode=0, out_cap=4096):
+def _postprocess(dets_list, method, thresh=0.4, mode=0, out_cap=None):
     B = len(dets_list)
     cap = max(1, max(len(d) for d in dets_list))
+    out_cap = out_cap or cap
     flat = np.zeros((B, cap, 5), F32)
     for i, d in enumerate(dets_list):
         flat[i, :len(d)] = d
@@ -466,6 +468,7 @@ def _postprocess(dets_list, method, thresh=0.4, mode=0, out_cap=4096):
     L.call("shf_postprocess", _ptr(dev(flat)), _ptr(dev(seg_b)), _ptr(dev(seg_e)), B, cap, float(thresh), method, mode,
            _ptr(oi), _ptr(od), _ptr(oc), out_cap, _ptr(ws), ws_bytes, _stream())
     cnt = oc.cpu().numpy()
+    assert (cnt <= out_cap).all(), "out_count is the TRUE count; the caller sized out_cap too small"
     if method == 0:
         return [oi[i, :cnt[i]].cpu().numpy().tolist() for i in range(B)]
     return [od[i, :cnt[i]].cpu().numpy() for i in range(B)]
@@ -482,6 +485,83 @@ def test_nms_indices_bit_exact_vs_reference_golden(golden_dir):
     got = _postprocess([g["grid_dets"], g["n300_dets"]], 0, 0.4, mode=1)
     assert got[0] == OP.nms(g["grid_dets"], 0.4, OP.NMS_GPU) and got[1] == OP.nms(g["n300_dets"], 0.4, OP.NMS_GPU)
     assert _postprocess([np.zeros((0, 5), F32)], 0)[0] == []
+
+
+def _clustered_dets(n, seed, centers=None, score_ties=False):
+    """n detections jittered around a few hundred face-like centres (so greedy clusters have 1..dozens of members)."""
+    rng = np.random.RandomState(seed)
+    k = centers or max(1, n // 12)
+    c = rng.rand(k, 2) * 900 + 40
+    size = rng.rand(k) * 60 + 12
+    which = rng.randint(0, k, n)
+    ctr = c[which] + rng.randn(n, 2) * (size[which, None] * 0.15)
+    wh = size[which, None] * (1 + rng.randn(n, 2) * 0.12)
+    d = np.hstack([ctr - wh / 2, ctr + wh / 2, rng.rand(n, 1) * 0.94 + 0.051]).astype(F32)
+    if score_ties:
+        d[:, 4] = np.round(d[:, 4] * 20) / 20 + F32(0.001)           # many exactly equal scores
+    return d
+
+
+@pytest.mark.parametrize("method", [0, 1], ids=["nms", "vote"])
+def test_postprocess_ragged_batch_mask_and_serial_paths_vs_oracle(method):
+    """One batched call over images with 0 .. 20000 rows: the small ones take the IoU bit-mask kernels (block edges at
+    63/64/65/128/129 rows), the ones above 16384 rows the serial sweep; every image must equal the oracle (NMS keep lists
+    bit-exact, voted boxes to float32 sum order)."""
+    sizes = [0, 1, 2, 63, 64, 65, 128, 129, 1000, 5000, 16384, 16385, 20000]
+    dets = [_clustered_dets(n, 100 + i) if n else np.zeros((0, 5), F32) for i, n in enumerate(sizes)]
+    got = _postprocess(dets, method, 0.4, mode=0)
+    for n, d, g in zip(sizes, dets, got):
+        if method == 0:
+            assert g == OP.nms(d, 0.4, OP.NMS_CPU), n
+        else:
+            ref = OP.bbox_vote(d.copy(), 0.4)
+            assert g.shape == ref.shape, (n, g.shape, ref.shape)
+            assert np.abs(g[:, :4] - ref[:, :4]).max() < 2e-3 and np.abs(g[:, 4] - ref[:, 4]).max() < 1e-6, n
+
+
+def test_postprocess_score_ties_and_signed_scores():
+    """Ties resolve to the lower row (the oracle's stated order) through sort, NMS and voting; scores of any sign sort
+    correctly (the nms drop-ins accept arbitrary user scores, e.g. logits)."""
+    d = _clustered_dets(3000, 7, score_ties=True)
+    assert len(np.unique(d[:, 4])) < 40
+    assert _postprocess([d], 0, 0.4, mode=0)[0] == OP.nms(d, 0.4, OP.NMS_CPU)
+    ref = OP.bbox_vote(d.copy(), 0.4)
+    got = _postprocess([d], 1, 0.4)[0]
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-3
+    neg = _clustered_dets(2000, 8)
+    neg[:, 4] = np.random.RandomState(9).randn(2000).astype(F32) * 3          # logits: both signs, wide range
+    for mode, omode in ((0, OP.NMS_CPU), (1, OP.NMS_GPU)):
+        assert _postprocess([neg], 0, 0.5, mode=mode)[0] == OP.nms(neg, 0.5, omode)
+
+
+def test_segmented_sort_ragged_segments_and_sentinels():
+    """shf_sort_keys directly: several segments of different lengths in one launch, sentinels dropped, the 32 score bits
+    sorted stably (tile edges at 4096 keys; begin_bit 32 and the batched layout's 27)."""
+    rng = np.random.RandomState(5)
+    stride = 3 * 4096 + 77
+    lens = np.array([0, 1, 31, 4096, 4097, stride, 9000], np.int32)
+    S = len(lens)
+    for begin_bit in (32, 27):
+        row_bits = begin_bit
+        score = rng.randint(0, 1 << 20, (S, stride)).astype(np.uint64) << np.uint64(7)       # many duplicate fields
+        score[rng.rand(S, stride) < 0.6] = np.uint64(0xffffffff)                              # sentinels
+        rows = np.tile(np.arange(stride, dtype=np.uint64), (S, 1))
+        keys = (score << np.uint64(row_bits)) | rows
+        if begin_bit == 27:
+            keys |= (np.arange(S, dtype=np.uint64)[:, None] & np.uint64(31)) << np.uint64(59)
+        kin = dev(keys.view(np.int64))
+        kout = torch.zeros_like(kin)
+        ws_bytes = int(L.load().shf_sort_keys_workspace(S * stride))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=DEV)
+        L.call("shf_sort_keys", _ptr(kin), _ptr(kout), S, stride, _ptr(dev(lens)), stride, begin_bit, _ptr(ws), ws_bytes,
+               _stream())
+        out = kout.cpu().numpy().view(np.uint64)
+        assert torch.equal(kin, dev(keys.view(np.int64)))                                     # input untouched
+        for sgm in range(S):
+            k = keys[sgm, :lens[sgm]]
+            k = k[((k >> np.uint64(begin_bit)) & np.uint64(0xffffffff)) != np.uint64(0xffffffff)]
+            assert np.array_equal(out[sgm, :len(k)], np.sort(k, kind="stable")), (begin_bit, sgm)
+            assert (out[sgm, len(k):lens[sgm]] == np.uint64(0xffffffffffffffff)).all()
 
 
 def test_nms_host_abi_symbol(golden_dir):

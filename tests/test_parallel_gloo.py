@@ -1,5 +1,5 @@
-"""world_size-2 CPU test (gloo) of the multi-GPU exchange: the reference partition + one all_gather of the
-fixed-capacity box buffers, merged in rank order (lib/test.py:324-344)."""
+"""world_size-2 CPU test (gloo) of the multi-GPU exchange: the reference partition + ONE all_gather of the packed
+(count | boxes) buffers, merged in rank order (lib/test.py:324-344); overflowing the payload raises."""
 import os
 import socket
 
@@ -41,10 +41,24 @@ def _worker(rank, world, port, n_images, out_dir):
         d, n = _fake_result(idx)
         dets[j] = torch.from_numpy(d)
         cnts[j] = n
-    gd, gc = gather_detections(dets, cnts, world)
-    merged = merge_gathered(gd, gc, n_images, world)
+    calls = []
+    orig = dist.all_gather
+    dist.all_gather = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    g = gather_detections(dets, cnts, world)
+    dist.all_gather = orig
+    assert len(calls) == 1 and tuple(g.shape) == (world, per, 17, 5)          # one collective, counts ride in row 0
+    merged = merge_gathered(g, n_images, world)
     if rank == 0:
         np.savez(os.path.join(out_dir, "merged.npz"), *merged)
+        small = gather_detections(dets, cnts, world, rows=4)                  # (collective: both ranks must take part)
+        try:
+            merge_gathered(small, n_images, world)
+            ok = all(_fake_result(i)[1] <= 4 for i in range(n_images))
+        except RuntimeError as e:
+            ok = "gather_rows" in str(e)
+        assert ok
+    else:
+        gather_detections(dets, cnts, world, rows=4)
     dist.barrier()
     dist.destroy_process_group()
 
