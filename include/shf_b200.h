@@ -181,6 +181,9 @@ void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, i
           int device_id);
 int shf_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim, double thresh,
                  int mode, int device_id);
+/* lib/test.py:181-217 `bbox_vote(det)` with the same host-buffer contract: dets_host (num_dets x 5 float32, any order) ->
+ * out_dets (caller-allocated, >= num_dets / 2 + 1 rows of 5 floats), *num_out rows; synchronous. */
+int shf_bbox_vote_host(float* out_dets, int* num_out, const float* dets_host, int num_dets, double thresh, int device_id);
 
 /* lib/utils/bbox.pyx: kind 0 bbox_overlaps (:14-54), 1 bbox_overlaps_IoA (:56-102), 2 bbox_overlaps_itself
  * (:106-142).  boxes (n,4), query (k,4), out (n,k): float64 [dev]. */

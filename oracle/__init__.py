@@ -1,6 +1,6 @@
 """ORACLE -- test infrastructure, NOT product code.
 
-A CPU restatement of the reference's algorithm for the inference hot path (every function cites the
+A CPU (NumPy) restatement of the reference's algorithm for the inference hot path (every function cites the
 reference file:line it follows), pinned against golden vectors produced by the reference's own code
 (tests/golden/make_golden.py) and against the vendored Caffe's known-answer tests
 (tests/test_oracle_kat.py).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
@@ -13,21 +13,3 @@ a17 cpu_nms/py_cpu_nms and a18 bbox_overlaps pinned bit-exactly by outputs of th
 modules run in this container.  The vendored Caffe itself cannot be built here, so the
 conv stack has no end-to-end golden from the original binary.
 """
-import os
-import subprocess
-
-_HERE = os.path.dirname(os.path.abspath(__file__))
-
-
-def build():
-    """Compile oracle/c/*.c -> oracle/_build/liboracle.so (plain C restatement of NMS / box voting /
-    IoU used as the timed CPU baseline's post-processing)."""
-    src = os.path.join(_HERE, "c", "oracle_post.c")
-    if not os.path.exists(src):
-        return None
-    out_dir = os.path.join(_HERE, "_build")
-    os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "liboracle.so")
-    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src, "-lm"])
-    return out

@@ -63,6 +63,7 @@ SIGNATURES = {
     "_nms": (None, [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_float), c_int, c_int, c_float, c_int]),
     "shf_nms_host": (c_int, [C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_float), c_int, c_int, c_double, c_int,
                              c_int]),
+    "shf_bbox_vote_host": (c_int, [C.POINTER(c_float), C.POINTER(c_int), C.POINTER(c_float), c_int, c_double, c_int]),
     "shf_bbox_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "shf_debug_conv_direct": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

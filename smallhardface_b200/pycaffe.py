@@ -33,6 +33,11 @@ def _env_fast_min_scale():
     return None if v in ("none", "off", "") else float(v)
 
 
+def _now():
+    import time
+    return time.perf_counter()
+
+
 _state = {"device": 0, "mode": "gpu", "fast_min_scale": _env_fast_min_scale()}
 
 
@@ -153,6 +158,7 @@ class Net(object):
         self.top_names = OrderedDict((l.name, list(l.tops)) for l in self._spec.layers)
         self.bottom_names = OrderedDict((l.name, list(l.bottoms)) for l in self._spec.layers)
         import torch
+        self._prof = None
         self._out_host = None                                   # page-locked mirror of the packed result block (grow-only)
         self._guard_host = torch.zeros(tuple(self._engine.guard.shape), dtype=torch.int32,
                                        pin_memory=torch.cuda.is_available())
@@ -169,6 +175,8 @@ class Net(object):
         if start is not None or end is not None:
             raise NotImplementedError("partial forward(start=, end=) is not on the inference hot path")
         import torch
+        prof = self._prof                                       # bench.py: where a forward's host time goes
+        t0 = _now() if prof is not None else 0.0
         if kwargs:
             if set(kwargs.keys()) != set(self.inputs):
                 raise Exception("Input blob arguments do not match net inputs.")
@@ -186,6 +194,7 @@ class Net(object):
             self._spec.infer_shapes({self.inputs[0]: data_blob.shape})
         info = (float(info[0]), float(info[1]), float(info[2]))
         stream = torch.cuda.current_stream()
+        t1 = _now() if prof is not None else 0.0
         for attempt in (0, 1):
             eng.guard.zero_()
             # `.data` of an input blob is page-locked: the upload reads it directly (valid until the sync below)
@@ -195,6 +204,7 @@ class Net(object):
                 if self._out_host is None or self._out_host.numel() < pack.numel():
                     self._out_host = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
                 self._out_host[:pack.numel()].copy_(pack, non_blocking=True)
+            t2 = _now() if prof is not None else 0.0
             stream.synchronize()                                 # the one synchronisation of the forward
             # a fast-format level outside the format's exponent window: the engine has switched itself to split fp16
             # (sticky); repeat this forward there.  fp16 overflow raises.
@@ -215,7 +225,14 @@ class Net(object):
             if len(tops) > 1:
                 self._set_host(tops[1], host[4 + 5 * topn:4 + 7 * topn].reshape(topn, 2)[:R])
         outs = set(self.outputs + list(blobs or []))
-        return {out: self.blobs[out].data for out in outs}
+        res = {out: self.blobs[out].data for out in outs}
+        if prof is not None:
+            t3 = _now()
+            prof["assign_s"] = prof.get("assign_s", 0.0) + (t1 - t0)      # caller's array -> page-locked input blob
+            prof["enqueue_s"] = prof.get("enqueue_s", 0.0) + (t2 - t1)    # upload + graph launch + download, enqueued
+            prof["wait_s"] = prof.get("wait_s", 0.0) + (t3 - t2)          # GPU (H2D + kernels + D2H) not hidden by the host
+            prof["forwards"] = prof.get("forwards", 0) + 1
+        return res
 
     @staticmethod
     def _assign(blob, arr):
