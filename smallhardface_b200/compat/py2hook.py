@@ -59,7 +59,7 @@ def transform_source(src: str, filename: str = "<src>") -> str:
             s = re.sub(r"\b%s\b" % a, b, s)
     s = re.sub(r"(\w[\w\.\[\]'\"]*)\.has_key\(([^()]*)\)", r"(\2 in \1)", s)
     s = s.replace(".iteritems()", ".items()").replace(".itervalues()", ".values()").replace(".iterkeys()", ".keys()")
-    s = re.sub(r"open\(([^()]*?),\s*'w',\s*0\)", r"open(\1, 'w', 1)", s)       # unbuffered text mode
+    s = re.sub(r",\s*'w',\s*0\)", r", 'w', 1)", s)                             # open(..., 'w', 0): unbuffered text mode
     s = re.sub(r"except\s+([\w\.]+)\s*,\s*(\w+)\s*:", r"except \1 as \2:", s)
     # true-division results used as integers on the test path
     s = s.replace("scores.shape[1] / (A * self._num_feats)", "scores.shape[1] // (A * self._num_feats)")

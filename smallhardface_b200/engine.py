@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from . import lib as L
-from .graph import NetSpec, LayerSpec, fold_batchnorm_scale, parse_python_param_str
+from .graph import NetSpec, LayerSpec, PROPOSAL_LAYER, fold_batchnorm_scale, parse_python_param_str
 
 F32 = np.float32
 
@@ -225,8 +225,8 @@ class GpuNet:
         # ---- detection tail pattern ---------------------------------------------------------------
         for l in layers:
             if l.type == "Python":
-                if (l.p["module"], l.p["layer"]) != ("lib.layers.proposal_layer", "ProposalLayer"):
-                    raise L.ShfError("Python layer %s.%s has no CUDA implementation on this path" % (l.p["module"], l.p["layer"]))
+                if (l.p["module"], l.p["layer"]) != PROPOSAL_LAYER:
+                    continue               # generic caffe.Layer protocol: a host round trip per forward (see "python" ops)
                 if self.tail is not None:
                     # the reference's multi-module form (boxes_<level> / cls_prob_<level>, lib/test.py:67-106) is not deployed
                     # by any shipped config; refuse it instead of silently keeping the last ProposalLayer
@@ -252,6 +252,7 @@ class GpuNet:
                     off += c
         # ---- body ops ----------------------------------------------------------------------------------
         self.ops: List[Tuple[str, LayerSpec, dict]] = []
+        self.has_python = False
         self.fused_blobs = set()
         i = 0
         dev = self.device
@@ -325,6 +326,15 @@ class GpuNet:
                         continue
                     self.ops.append(("conv", l, st))
                 i = j + (1 if relu else 0)
+                continue
+            if l.type == "Python":
+                # Any Python layer other than the ProposalLayer runs through the generic protocol of
+                # caffe/include/caffe/layers/python_layer.hpp:19-43 (reshape + forward on host blobs): its bottoms are
+                # downloaded as fp32 NCHW, its tops uploaded for whatever consumes them.  This is the reference's own
+                # mechanism for such layers (PythonLayer is CPU-only in Caffe), not a fallback of a hot-path layer.
+                self.ops.append(("python", l, {}))
+                self.has_python = True
+                i += 1
                 continue
             if l.type in ("BatchNorm", "Scale"):
                 raise L.ShfError("%s %s does not follow a convolution it can be folded into (unsupported pattern)" % (l.type, l.name))
@@ -495,22 +505,36 @@ class GpuNet:
             return None
         return self.run_tail(0, im_info, dets, pass_offsets, pass_idx, det_cap, flip, det_thresh)
 
-    def forward_body(self, data: torch.Tensor, fast: bool = False):
+    def forward_body(self, data: Optional[torch.Tensor], fast: bool = False, extra_inputs=None, op_range=None, preset=None):
         """Runs every layer up to the detection tail on a batch (N,3,H,W); blobs stay on the device in
         ``self.tensors``.  The ProposalLayer is per image (``proposal_layer.py:74-75``): call ``run_tail(n, ...)``.
-        ``fast``: activations (and conv operands) in the hf8 format instead of split fp16."""
+        ``fast``: activations (and conv operands) in the hf8 format instead of split fp16.
+        ``extra_inputs``: {name: tensor} for further net inputs; ``op_range`` = (first, last) indices into ``self.ops`` and
+        ``preset`` = {blob: fp32 NCHW tensor} serve ``forward(start=, end=)`` (pycaffe.py:88-134)."""
         if fast and self.fast_min_scale is None:
             raise L.ShfError("this GpuNet was built without the fast operand format (fast_min_scale=None)")
         fmt = FMT_HF8 if fast else FMT_H2
         T = self.tensors = OrderedDict()          # a fresh table: a captured graph keeps the one it was recorded with
-        T["data"] = data
+        if data is not None and self.spec.inputs:
+            T[self.spec.inputs[0]] = data
+        for k, v in (extra_inputs or {}).items():
+            T[k] = v
+        for k, v in (preset or {}).items():
+            T[k] = v
         st = _stream()
-        for kind, l, s in self.ops:
+        ops = self.ops if op_range is None else self.ops[op_range[0]:op_range[1] + 1]
+        for kind, l, s in ops:
             if kind == "alias":
                 for t in l.tops:
                     T[t] = T[l.bottoms[0]]
                 continue
+            if kind == "python":
+                self._run_python_layer(l, T)
+                continue
             x = T[l.bottoms[0]]
+            if kind != "conv1" and not isinstance(x, H2):
+                # a blob that arrived as fp32 NCHW (a Python layer's top, or a host-written blob of forward(start=))
+                x = H2.from_nchw(x.to(self.device), fmt)
             if kind == "conv1":
                 n, _, h, w = x.shape
                 out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
@@ -561,6 +585,50 @@ class GpuNet:
                 L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
                        s["pad"], out.ctot, out.c_off, x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
             self.launches += 1
+
+    def _run_python_layer(self, l: LayerSpec, T):
+        """``PythonLayer::Reshape`` + ``Forward_cpu`` (python_layer.hpp:34-43) on host blobs."""
+        st = self.spec.py_layers.get(l.name)
+        if st is None:
+            self.spec.infer_shapes({})
+            st = self.spec.py_layers[l.name]
+        for blob, name in zip(st["bottoms"], l.bottoms):
+            src = T[name]
+            if isinstance(src, H2):
+                src = src.to_nchw()
+            arr = src.detach().cpu().numpy() if torch.is_tensor(src) else np.asarray(src, dtype=F32)
+            blob.reshape(*arr.shape)
+            blob.data[...] = arr
+        st["obj"].reshape(st["bottoms"], st["tops"])
+        st["obj"].forward(st["bottoms"], st["tops"])
+        for blob, name in zip(st["tops"], l.tops):
+            T[name] = torch.from_numpy(blob.data)
+
+    def op_span(self, start_layer: Optional[str], end_layer: Optional[str]):
+        """Indices (first, last) of the launches that realise layers ``start_layer`` .. ``end_layer`` (inclusive).  The
+        plan fuses Convolution + ReLU (+ Pooling) and folds BatchNorm / Scale, so the range must begin and end on launch
+        boundaries; anything else raises."""
+        names = [l.name for l in self.spec.layers]
+        lo = names.index(start_layer) if start_layer is not None else 0
+        hi = names.index(end_layer) if end_layer is not None else len(names) - 1
+        if self.tail is not None and any(n in self.tail["fused"] or n == self.tail["name"] for n in names[lo:hi + 1]):
+            raise L.ShfError("forward(start=, end=): the detection tail is one fused launch; end the range before it "
+                             "or run the whole net")
+        idx_of = {n: i for i, n in enumerate(names)}
+        first = [idx_of[l.name] for _, l, _ in self.ops]
+        absorbed = ("ReLU", "Pooling", "BatchNorm", "Scale")      # what a conv launch may have swallowed after itself
+        op_layers = []
+        for oi, f in enumerate(first):
+            nxt = first[oi + 1] if oi + 1 < len(first) else len(names)
+            op_layers.append([li for li in range(f, nxt) if li == f or self.spec.layers[li].type in absorbed])
+        inside = [oi for oi, lis in enumerate(op_layers) if any(lo <= li <= hi for li in lis)]
+        if not inside:
+            raise L.ShfError("forward(start=%r, end=%r) selects no launch" % (start_layer, end_layer))
+        for oi in inside:
+            if min(op_layers[oi]) < lo or max(op_layers[oi]) > hi:
+                raise L.ShfError("forward(start=%r, end=%r) cuts through a fused launch (%s .. %s run as one kernel)"
+                                 % (start_layer, end_layer, names[min(op_layers[oi])], names[max(op_layers[oi])]))
+        return inside[0], inside[-1]
 
     def run_tail(self, n_img, im_info, dets=None, pass_offsets=None, pass_idx=0, det_cap=0, flip=False, det_thresh=0.05):
         """Detection tail for image ``n_img`` of the last ``forward_body`` batch."""
@@ -634,7 +702,7 @@ class GpuNet:
         if ent is None:
             x = torch.empty(tuple(data_src.shape), dtype=torch.float32, device=self.device)
             x.copy_(data_src, non_blocking=True)
-            if os.environ.get("SHF_CUDA_GRAPHS", "1") == "0" or self.profile:
+            if os.environ.get("SHF_CUDA_GRAPHS", "1") == "0" or self.profile or self.has_python:
                 res = self.forward(x, info)
                 return None if res is None else self.last_pack
             # eager warm-up (function attributes, the persistent tail buffers), then the capture

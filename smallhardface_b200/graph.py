@@ -36,6 +36,65 @@ class LayerSpec:
     msg: Optional[cp.Msg] = None
 
 
+PROPOSAL_LAYER = ("lib.layers.proposal_layer", "ProposalLayer")      # executed by the fused CUDA tail, never instantiated
+
+
+class PyBlob:
+    """What a generic ``caffe.Layer`` sees as ``bottom[i]`` / ``top[i]``: the ``caffe.Blob`` attributes exposed by
+    ``caffe/python/caffe/_caffe.cpp:453-488`` over a host float32 array."""
+
+    def __init__(self, shape=()):
+        self.data = np.zeros(tuple(int(d) for d in shape), dtype=np.float32)
+        self._diff = None
+
+    def reshape(self, *dims):
+        dims = tuple(int(d) for d in dims)
+        if dims != self.data.shape:
+            self.data = np.zeros(dims, dtype=np.float32)
+            self._diff = None
+
+    @property
+    def diff(self):
+        if self._diff is None or self._diff.shape != self.data.shape:
+            self._diff = np.zeros_like(self.data)
+        return self._diff
+
+    shape = property(lambda self: tuple(self.data.shape))
+    count = property(lambda self: int(self.data.size))
+
+    def _legacy(self, i):
+        if self.data.ndim > 4:
+            raise ValueError("Cannot use legacy accessors on Blobs with > 4 axes.")
+        return int(self.data.shape[i]) if i < self.data.ndim else 1
+    num = property(lambda self: self._legacy(0))
+    channels = property(lambda self: self._legacy(1))
+    height = property(lambda self: self._legacy(2))
+    width = property(lambda self: self._legacy(3))
+
+
+class _LayerBlobs(list):
+    """``layer.blobs`` of a Python layer (``python_layer.hpp`` exposes the Layer's blob vector; ``add_blob(*dims)``)."""
+
+    def add_blob(self, *dims):
+        self.append(PyBlob(dims))
+
+
+def make_python_layer(spec: "LayerSpec", phase: int, bottom_shapes):
+    """``PythonLayer::LayerSetUp`` (``caffe/include/caffe/layers/python_layer.hpp:19-32``): import ``module``, build
+    ``layer``, hand it ``param_str`` and ``phase``, call ``setup(bottom, top)`` once with shaped bottoms."""
+    import importlib
+    mod = importlib.import_module(spec.p["module"])
+    obj = getattr(mod, spec.p["layer"])()
+    obj.param_str = spec.p["param_str"]
+    obj.phase = phase
+    if not hasattr(obj, "blobs") or obj.blobs is None:
+        obj.blobs = _LayerBlobs()
+    bottoms = [PyBlob(s) for s in bottom_shapes]
+    tops = [PyBlob() for _ in spec.tops]
+    obj.setup(bottoms, tops)
+    return dict(obj=obj, bottoms=bottoms, tops=tops)
+
+
 def _pair(rep, h, w, default, what, lname):
     """ConvolutionParameter's repeated/ _h/_w forms -> (h, w) (``base_conv_layer.cpp:33-92``)."""
     if h is not None or w is not None:
@@ -117,6 +176,7 @@ class NetSpec:
         self.blob_names: List[str] = []
         self.inputs: List[str] = []
         self.input_shapes: Dict[str, Tuple[int, ...]] = {}
+        self.py_layers: Dict[str, dict] = {}           # generic Python layers: name -> {obj, bottoms, tops} (lazy, see infer_shapes)
         self.param_owner: Dict[str, str] = {}          # named param -> storage key
         self.param_shapes: Dict[str, Tuple[int, ...]] = {}
         produced: "OrderedDict[str, bool]" = OrderedDict()    # blob -> consumed?
@@ -276,10 +336,21 @@ class NetSpec:
             elif t == "Reshape":
                 out = reshape_shape(bs[0], spec.p["dims"], spec.p["axis"], spec.p["num_axes"], spec.name)
             elif t == "Python":
-                # ProposalLayer.setup: rois (1,5), scores (1,1,1,1) until the first forward
-                out = None
-                for i, nm in enumerate(spec.tops):
-                    shapes[nm] = (1, 5) if i == 0 else (1, 2)
+                if (spec.p["module"], spec.p["layer"]) == PROPOSAL_LAYER:
+                    # ProposalLayer.setup: rois (1,5), scores (1,1,1,1) until the first forward
+                    for i, nm in enumerate(spec.tops):
+                        shapes[nm] = (1, 5) if i == 0 else (1, 2)
+                    continue
+                # any other Python layer: the generic protocol (python_layer.hpp:19-43) -- instantiate once (setup),
+                # then ask its reshape() for the top shapes, exactly what Net::Reshape does
+                st = self.py_layers.get(spec.name)
+                if st is None:
+                    st = self.py_layers[spec.name] = make_python_layer(spec, self.phase, bs)
+                for blob, shp in zip(st["bottoms"], bs):
+                    blob.reshape(*shp)
+                st["obj"].reshape(st["bottoms"], st["tops"])
+                for nm, blob in zip(spec.tops, st["tops"]):
+                    shapes[nm] = blob.shape
                 continue
             else:                                                   # pragma: no cover
                 raise AssertionError(t)

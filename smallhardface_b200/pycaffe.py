@@ -173,7 +173,7 @@ class Net(object):
         the page-locked input blob, one upload, one CUDA-graph launch (engine.GpuNet.forward_cached), one download of
         the packed (rows | boxes | cls_prob) block + the range guard, one synchronisation."""
         if start is not None or end is not None:
-            raise NotImplementedError("partial forward(start=, end=) is not on the inference hot path")
+            return self._forward_range(blobs, start, end, kwargs)
         import torch
         prof = self._prof                                       # bench.py: where a forward's host time goes
         t0 = _now() if prof is not None else 0.0
@@ -186,8 +186,10 @@ class Net(object):
                 self._assign(self.blobs[in_], blob)              # blob.data[...] = arr, as pycaffe
         eng = self._engine
         eng.cfg.update(_hot_path_cfg())
+        if eng.tail is None or eng.has_python or len(self.inputs) != 2:
+            return self._forward_generic(blobs)
         data_blob = self.blobs[self.inputs[0]]
-        info = self.blobs[self.inputs[1]]._host.reshape(-1) if len(self.inputs) > 1 else np.array([0, 0, 1], np.float32)
+        info = self.blobs[self.inputs[1]]._host.reshape(-1)
         n, c, h, w = data_blob.shape
         if (h % 16) or (w % 16):
             # concat_layer.cpp:40-44 would fail the same way inside Caffe's Reshape
@@ -233,6 +235,73 @@ class Net(object):
             prof["wait_s"] = prof.get("wait_s", 0.0) + (t3 - t2)          # GPU (H2D + kernels + D2H) not hidden by the host
             prof["forwards"] = prof.get("forwards", 0) + 1
         return res
+
+    def _forward_generic(self, blobs=None):
+        """Nets without the detection tail, with generic Python layers, or with other input sets: every launch eagerly
+        (no CUDA graph: Python layers run on the host in the middle of the net), outputs synchronised lazily by `.data`."""
+        import torch
+        eng = self._engine
+        dev = eng.device
+        ins = {name: self.blobs[name]._tview.to(dev, non_blocking=True) for name in self.inputs}
+        shapes = self._spec.infer_shapes({name: self.blobs[name].shape for name in self.inputs})
+        first = ins.pop(self.inputs[0]) if self.inputs else None
+        eng.guard.zero_()
+        eng.forward_body(first, fast=False, extra_inputs=ins)
+        res = None
+        if eng.tail is not None:
+            info = self.blobs[eng.tail["info"]]._host.reshape(-1)
+            res = eng.run_tail(0, (float(info[0]), float(info[1]), float(info[2])))
+        torch.cuda.current_stream().synchronize()
+        eng.check_ranges()
+        for name, b in self.blobs.items():
+            b._stale = name not in self.inputs
+        if res is not None:
+            boxes, probs, rows = res
+            R = int(rows.item())
+            self._set_host(eng.tail["tops"][0], boxes[:R].cpu().numpy())
+            if len(eng.tail["tops"]) > 1:
+                self._set_host(eng.tail["tops"][1], probs[:R].cpu().numpy())
+        del shapes
+        outs = set(self.outputs + list(blobs or []))
+        return {out: self.blobs[out].data for out in outs}
+
+    def _forward_range(self, blobs, start, end, kwargs):
+        """``net.forward(start=, end=)`` (pycaffe.py:88-134, test: caffe/python/caffe/test/test_net.py:74-90): run only the
+        layers start..end, reading their bottoms from the blobs' CURRENT contents (whatever the caller wrote through
+        ``.data``) and returning the tops of ``end``.  The range must fall on launch boundaries of the fused plan."""
+        import torch
+        eng = self._engine
+        if kwargs:
+            if set(kwargs.keys()) != set(self.inputs):
+                raise Exception("Input blob arguments do not match net inputs.")
+            for in_, blob in kwargs.items():
+                self._assign(self.blobs[in_], blob)
+        if start is not None and start not in self._layer_names:
+            raise ValueError("%r is not in list" % start)             # list.index() in pycaffe
+        if end is not None and end not in self._layer_names:
+            raise ValueError("%r is not in list" % end)
+        first_op, last_op = eng.op_span(start, end)
+        produced, needed = set(), []
+        for kind, l, st in eng.ops[first_op:last_op + 1]:
+            for b in l.bottoms:
+                if b not in produced and b not in needed:
+                    needed.append(b)
+            produced.update(l.tops)
+            if "top" in st:
+                produced.add(st["top"])
+            if "pool_top" in st:
+                produced.add(st["pool_top"])
+        preset = {b: torch.from_numpy(np.ascontiguousarray(self.blobs[b].data)).to(eng.device) for b in needed}
+        eng.guard.zero_()
+        eng.forward_body(None, fast=False, op_range=(first_op, last_op), preset=preset)
+        torch.cuda.current_stream().synchronize()
+        eng.check_ranges()
+        for name in produced:
+            if name in self.blobs and name in eng.tensors:
+                self.blobs[name]._stale = True
+        tops = self.top_names[end] if end is not None else self.outputs
+        outs = set(list(tops) + list(blobs or []))
+        return {out: self.blobs[out].data for out in outs}
 
     @staticmethod
     def _assign(blob, arr):
@@ -280,8 +349,15 @@ class _ParamBlob(object):
 
 
 class Layer(object):
-    """``caffe.Layer`` base for Python layers (``python_layer.hpp:19-43``).  The only Python layer on the test
-    path, ``lib.layers.proposal_layer.ProposalLayer``, is executed by the fused CUDA tail and never instantiated."""
+    """``caffe.Layer``: base class of Python layers (``caffe/include/caffe/layers/python_layer.hpp:19-43``, exposed by
+    ``_caffe.cpp:420-430``).  The net builds ``module.layer()``, sets ``param_str`` and ``phase``, calls
+    ``setup(bottom, top)`` once, then ``reshape(bottom, top)`` + ``forward(bottom, top)`` per forward with Blob-like
+    bottoms / tops (``smallhardface_b200.graph.PyBlob``: ``.data``, ``.diff``, ``.reshape``, ``.shape``, ``.num`` ...).
+    The one Python layer on the test path, ``lib.layers.proposal_layer.ProposalLayer``, is matched by name and runs as
+    the fused CUDA tail instead; every other subclass goes through this protocol on host blobs, as in Caffe."""
+    param_str = ""
+    phase = TEST
+    blobs = None
 
     def setup(self, bottom, top):
         pass
@@ -294,6 +370,12 @@ class Layer(object):
 
     def backward(self, top, propagate_down, bottom):
         pass
+
+
+def layer_type_list():
+    """``caffe.layer_type_list()`` (``_caffe.cpp:380``): the layer types this build executes."""
+    from .graph import SUPPORTED
+    return list(SUPPORTED)
 
 
 def _training_only(name):

@@ -49,7 +49,7 @@ def relerr(a, b):
 
 def test_library_loads_and_reports_b200():
     lib = L.load()
-    assert lib.shf_abi_version() == 2
+    assert lib.shf_abi_version() == L.ABI_VERSION
     sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
     L.call("shf_device_info", 0, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem))
     assert maj.value == 10, "built for sm_100a only"
