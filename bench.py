@@ -445,6 +445,11 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         plug_launches = plug.net._engine.launches - pl0 + 7 * BATCH * args.steps
+    wider = None
+    if args.wider_shaped > 0:                                 # BASELINE configs[4]: every rank takes part (one all-gather)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import wider_shaped_run
+        wider = wider_shaped_run.run(args.wider_shaped, kind=args.wider_partition, det=det)
     t = torch.tensor([ms, e2e_s * 1000.0, e2e_b_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -501,6 +506,8 @@ def run_ours(args):
                                    "h2d_bytes_per_step": int(sum(i.nbytes for i in imgs)), "d2h_bytes_per_step": int(n_out),
                                    "path": "Detector.detect(list of host uint8 images): one uint8 upload per image, device "
                                            "pyramid, levels batched over images x flips, device voting, boxes downloaded"}
+        if wider is not None:
+            line["wider_shaped"] = wider
         if not args.no_cpu_baseline:
             cores = host_threads()
             ips, desc = cpu_baseline(proto, model, imgs[0])
@@ -520,6 +527,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer legs")
+    ap.add_argument("--wider-shaped", type=int, default=0,
+                    help="also run BASELINE configs[4]: this many WIDER-val-shaped images sharded over the ranks (3226 = val)")
+    ap.add_argument("--wider-partition", default="reference", choices=["reference", "area_rr"])
     ap.add_argument("--ref-images", type=int, default=1, help="--impl reference: complete images in the timed region")
     ap.add_argument("--fast-min-scale", default=None,
                     help="operand-format policy override for trade-off tables: a number, or 'none' for split fp16 on every "

@@ -200,6 +200,7 @@ class GpuNet:
         self.device = torch.device(device)
         self.cfg = dict(pre_nms_topn=int(pre_nms_topn), score_thresh=float(score_thresh), min_size=float(min_size))
         self.launches = 0
+        self.nvtx = bool(os.environ.get("SHF_NVTX"))
         self.profile = False          # bench.py: bracket every tcgen05 conv launch with CUDA events
         self.events = []
         self._plan(params)
@@ -523,68 +524,79 @@ class GpuNet:
             T[k] = v
         st = _stream()
         ops = self.ops if op_range is None else self.ops[op_range[0]:op_range[1] + 1]
+        nvtx = self.nvtx
         for kind, l, s in ops:
-            if kind == "alias":
-                for t in l.tops:
-                    T[t] = T[l.bottoms[0]]
-                continue
-            if kind == "python":
-                self._run_python_layer(l, T)
-                continue
-            x = T[l.bottoms[0]]
-            if kind != "conv1" and not isinstance(x, H2):
-                # a blob that arrived as fp32 NCHW (a Python layer's top, or a host-written blob of forward(start=))
-                x = H2.from_nchw(x.to(self.device), fmt)
-            if kind == "conv1":
-                n, _, h, w = x.shape
-                out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
-                L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
-                       s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
-            elif kind == "conv":
-                if x.c_off != 0 or x.c != x.ctot:
-                    raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
-                fused = "pool_top" in s and x.h % 2 == 0 and x.w % 2 == 0
-                out = None
-                wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
-                if not fused or s["write_full"]:
-                    out = self._alloc_out(s["top"], x.n, x.h, x.w, s["cout"], fmt)
-                if self.profile:
-                    e0 = torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                if fused:
-                    pooled = self._alloc_out(s["pool_top"], x.n, x.h // 2, x.w // 2, s["cout"], fmt)
-                    if out is not None and out.fmt != pooled.fmt:
-                        raise L.ShfError("conv %s: full and pooled outputs need one format" % l.name)
-                    L.call("shf_conv_igemm_pool", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t if out else None),
-                           _ptr(pooled.t), x.n, x.h, x.w, s["cin"], s["cout"], s["k"], s["dil"],
-                           out.ctot if out else s["cout"], out.c_off if out else 0, pooled.ctot, pooled.c_off,
-                           s["scale"], int(s["relu"]), x.fmt, pooled.fmt, self._gptr(pooled.fmt, s["slot"]), st)
-                else:
-                    L.call("shf_conv_igemm", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
-                           s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt,
-                           self._gptr(out.fmt, s["slot"]), st)
-                    if "pool_top" in s:                      # odd size: pooling could not be fused
-                        if out.c_off != 0 or out.c != out.ctot:
-                            raise L.ShfError("pool after %s reads a channel window; not supported" % l.name)
-                        pooled = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, s["cout"], self.device, out.fmt)
-                        T[s["pool_top"]] = pooled
-                        L.call("shf_maxpool2x2", _ptr(out.t), _ptr(pooled.t), x.n, x.h, x.w, s["cout"], out.fmt, st)
-                        self.launches += 1
-                if self.profile:
-                    e1 = torch.cuda.Event(enable_timing=True)
-                    e1.record()
-                    self.events.append((e0, e1))
-            elif kind == "pool":
-                out = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c, self.device, x.fmt)
-                T[l.tops[0]] = out
-                L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, x.fmt, st)
-            elif kind == "deconv":
-                ho = s["s"] * (x.h - 1) + s["k"] - 2 * s["pad"]
-                wo = s["s"] * (x.w - 1) + s["k"] - 2 * s["pad"]
-                out = self._alloc_out(l.tops[0], x.n, ho, wo, x.c, fmt)
-                L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
-                       s["pad"], out.ctot, out.c_off, x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
-            self.launches += 1
+            if nvtx:                                   # SHF_NVTX=1: one named range per launch (nsys / ncu --nvtx)
+                torch.cuda.nvtx.range_push("%s:%s" % (kind, l.name))
+                try:
+                    self._run_op(kind, l, s, T, fmt, st)
+                finally:
+                    torch.cuda.nvtx.range_pop()
+            else:
+                self._run_op(kind, l, s, T, fmt, st)
+
+    def _run_op(self, kind, l, s, T, fmt, st):
+        if kind == "alias":
+            for t in l.tops:
+                T[t] = T[l.bottoms[0]]
+            return
+        if kind == "python":
+            self._run_python_layer(l, T)
+            return
+        x = T[l.bottoms[0]]
+        if kind != "conv1" and not isinstance(x, H2):
+            # a blob that arrived as fp32 NCHW (a Python layer's top, or a host-written blob of forward(start=))
+            x = H2.from_nchw(x.to(self.device), fmt)
+        if kind == "conv1":
+            n, _, h, w = x.shape
+            out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
+            L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
+                   s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+        elif kind == "conv":
+            if x.c_off != 0 or x.c != x.ctot:
+                raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
+            fused = "pool_top" in s and x.h % 2 == 0 and x.w % 2 == 0
+            out = None
+            wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
+            if not fused or s["write_full"]:
+                out = self._alloc_out(s["top"], x.n, x.h, x.w, s["cout"], fmt)
+            if self.profile:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if fused:
+                pooled = self._alloc_out(s["pool_top"], x.n, x.h // 2, x.w // 2, s["cout"], fmt)
+                if out is not None and out.fmt != pooled.fmt:
+                    raise L.ShfError("conv %s: full and pooled outputs need one format" % l.name)
+                L.call("shf_conv_igemm_pool", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t if out else None),
+                       _ptr(pooled.t), x.n, x.h, x.w, s["cin"], s["cout"], s["k"], s["dil"],
+                       out.ctot if out else s["cout"], out.c_off if out else 0, pooled.ctot, pooled.c_off,
+                       s["scale"], int(s["relu"]), x.fmt, pooled.fmt, self._gptr(pooled.fmt, s["slot"]), st)
+            else:
+                L.call("shf_conv_igemm", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"],
+                       s["cout"], s["k"], s["dil"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt,
+                       self._gptr(out.fmt, s["slot"]), st)
+                if "pool_top" in s:                      # odd size: pooling could not be fused
+                    if out.c_off != 0 or out.c != out.ctot:
+                        raise L.ShfError("pool after %s reads a channel window; not supported" % l.name)
+                    pooled = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, s["cout"], self.device, out.fmt)
+                    T[s["pool_top"]] = pooled
+                    L.call("shf_maxpool2x2", _ptr(out.t), _ptr(pooled.t), x.n, x.h, x.w, s["cout"], out.fmt, st)
+                    self.launches += 1
+            if self.profile:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.events.append((e0, e1))
+        elif kind == "pool":
+            out = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c, self.device, x.fmt)
+            T[l.tops[0]] = out
+            L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, x.fmt, st)
+        elif kind == "deconv":
+            ho = s["s"] * (x.h - 1) + s["k"] - 2 * s["pad"]
+            wo = s["s"] * (x.w - 1) + s["k"] - 2 * s["pad"]
+            out = self._alloc_out(l.tops[0], x.n, ho, wo, x.c, fmt)
+            L.call("shf_deconv_depthwise", _ptr(x.t), _ptr(s["w"]), _ptr(out.t), x.n, x.h, x.w, x.c, s["k"], s["s"],
+                   s["pad"], out.ctot, out.c_off, x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
+        self.launches += 1
 
     def _run_python_layer(self, l: LayerSpec, T):
         """``PythonLayer::Reshape`` + ``Forward_cpu`` (python_layer.hpp:34-43) on host blobs."""
