@@ -8,4 +8,4 @@ rm -rf _refdata/reference
 cp -r /root/reference _refdata/reference
 chmod -R u+w _refdata/reference
 trap 'rm -rf _refdata' EXIT
-/usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_reference_driver_remote.sh' 2>&1 | tail -30
+/usr/local/graft/bin/gpurun --timeout ${SHF_GPURUN_TIMEOUT:-1500} -- "${SHF_GPURUN_CMD:-bash tools/gpu_reference_driver_remote.sh}" 2>&1 | tail -40
