@@ -220,3 +220,35 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def wider_writer_inputs():
+    """Inputs of the detection-writer golden (tests/golden/wider_writer/): three WIDER-style relative paths; float64 rows,
+    an empty image, float32 rows; scores 1.0 and 1e-5 exercise '%g'."""
+    rng = np.random.RandomState(5)
+    paths = ['0--Parade/0_Parade_marchingband_1_465.jpg', '12--Group/12_Group_Group_12_Group_Group_12_10.jpg',
+             '2--Demonstration/2_Demonstration_Political_Rally_2_71.jpg']
+
+    def dets(n):
+        x = rng.rand(n, 2) * 900
+        wh = rng.rand(n, 2) * 200 + 3
+        sc = np.concatenate([rng.rand(n - 2), [1.0, 1e-5]]) if n >= 2 else rng.rand(n)
+        return np.hstack([x, x + wh, sc[:, None]]).astype(np.float64)
+    return paths, [dets(7), np.zeros((0, 5)), dets(3).astype(np.float32)]
+
+
+def make_wider_writer_golden(reference_root, out_dir):
+    """Runs the REFERENCE's own writer (lib/datasets/wider.py:143-170, imported unmodified through the py2 hook, cwd = the
+    reference root because lib/utils/get_config.py:25 reads configs/default.toml relatively) on a stub imdb."""
+    import shutil
+    os.chdir(reference_root)
+    from smallhardface_b200 import compat
+    compat.install(reference_root=reference_root)
+    import datasets.wider as W
+
+    class Stub(object):
+        pass
+    stub = Stub()
+    stub._image_paths, boxes = wider_writer_inputs()
+    shutil.rmtree(out_dir, ignore_errors=True)
+    W.wider.write_detections(stub, [[[] for _ in boxes], boxes], out_dir)

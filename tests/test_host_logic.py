@@ -314,3 +314,27 @@ def test_reference_python_files_import_unmodified_through_the_hook(tmp_path, mon
         sys.path[:] = [p for p in sys.path if not p.startswith(REF)]
         for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k.startswith("lib.") or k == "lib"]:
             del sys.modules[k]
+
+
+def test_detection_writer_byte_exact_vs_reference_golden(tmp_path):
+    """smallhardface_b200.writers against files written by the reference's own `wider.write_detections`
+    (tests/golden/wider_writer/, generated by tests/golden/make_golden.py:make_wider_writer_golden)."""
+    import importlib.util
+    from smallhardface_b200.writers import write_detections
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    paths, boxes = mg.wider_writer_inputs()
+    write_detections(paths, boxes, str(tmp_path))
+    gold = os.path.join(ROOT, "tests", "golden", "wider_writer")
+    n = 0
+    for root, _, files in os.walk(gold):
+        for f in files:
+            rel = os.path.relpath(os.path.join(root, f), gold)
+            assert open(os.path.join(str(tmp_path), rel), "rb").read() == open(os.path.join(root, f), "rb").read(), rel
+            n += 1
+    assert n == 3
+    # the general_* loader's variant: absolute paths with the leading slash stripped (general.py:52-53)
+    write_detections(["/data/a/im0.png"], [boxes[2]], str(tmp_path / "g"), extension="png", strip_leading_slash=True)
+    txt = open(os.path.join(str(tmp_path / "g"), "data", "a", "im0.txt")).read().splitlines()
+    assert txt[0] == "/data/a/im0.png" and txt[1] == "3" and len(txt) == 5 and txt[2].endswith(" ")

@@ -14,6 +14,13 @@ schemes:
                y = ah*wh  +  al8*wh8 + ah8*wl8        (one kind::f16 MMA + one K=32 kind::f8f6f4 MMA per 16 channels)
   h2f8       the first version: e5m2 activation bytes (al * 2^10, ah), weights e4m3(wh * 2^-10), e4m3(wl)
   h2f8c / h2f8e4 / h2f8e4b / cal   other e4m3 windows, incl. per-layer calibrated ones (study only)
+ schemes that would BREAK the 2-MMAs-per-MAC ceiling (study only; DESIGN.md "what would it take to pass 0.50"):
+  h15        1.5 MMAs: fp16 main term + ONE f8 correction al8*wh8 over 32 channels per instruction; the weight residual
+             term ah*wl is dropped, i.e. weights are plain fp16
+  h15q       1.5 MMAs: fp16 main term + both correction terms in 4-bit e2m1 ([al4 | ah4] x [wh4 | wl4], kind::mxf4 K = 64)
+  wino       Winograd F(2x2, 3x3) (2.25x fewer MACs) with the shipped hf8 operand split applied in the TRANSFORM domain:
+             V = B^T d B and U = G g G^T are split like activations / weights, M = sum_c U.V, Y = A^T M A in fp32
+             (3x3 stride-1 dilation-1 convs only; the dilated heads and the 1x1 convs stay direct hf8)
 
 usage: python tools/precision_model.py [level ...]      (levels = TEST.SCALES entries, default 100 300)
 """
@@ -45,6 +52,44 @@ def e4m3(t):
     return t.to(torch.float32).clamp(-448, 448).to(torch.float8_e4m3fn).to(F64)
 
 
+def e2m1(t):
+    """4-bit float (1 sign, 2 exponent, 1 mantissa): magnitudes {0, .5, 1, 1.5, 2, 3, 4, 6}, round to nearest, saturating."""
+    grid = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], dtype=F64)
+    a = t.to(F64).abs().clamp(max=6.0)
+    idx = (a.unsqueeze(-1) - grid).abs().argmin(dim=-1)
+    return torch.sign(t.to(F64)) * grid[idx]
+
+
+# Winograd F(2x2, 3x3) matrices (Lavin & Gray)
+_BT = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=F64)
+_G = torch.tensor([[1, 0, 0], [0.5, 0.5, 0.5], [0.5, -0.5, 0.5], [0, 0, 1]], dtype=F64)
+_AT = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=F64)
+
+
+def winograd_hf8(xt, ws):
+    """3x3 / pad 1 / stride 1 convolution of xt (1,C,H,W) with ws (K,C,3,3) (already scaled by 2^k) through
+    F(2x2,3x3), operands split hf8-style in the transform domain, products accumulated in float64."""
+    _, C, H, W = xt.shape
+    K = ws.shape[0]
+    Hp, Wp = H + (H % 2), W + (W % 2)
+    xp = torch.nn.functional.pad(xt, (1, 1 + Wp - W, 1, 1 + Hp - H))
+    tiles = xp.unfold(2, 4, 2).unfold(3, 4, 2)                       # (1, C, th, tw, 4, 4)
+    th, tw = tiles.shape[2], tiles.shape[3]
+    d = tiles.reshape(C, th * tw, 4, 4)
+    V = _BT @ d @ _BT.t()                                            # (C, T, 4, 4)
+    U = _G @ ws @ _G.t()                                             # (K, C, 4, 4)
+    vh = rn16(V)
+    val8, vah8 = e4m3((V - vh) * 64.0), e4m3(vh / 32.0)
+    uh = rn16(U)
+    uh8, ul8 = e4m3(uh / 64.0), e4m3((U - uh) * 32.0)
+    M = (torch.einsum("kcij,ctij->ktij", uh, vh) + torch.einsum("kcij,ctij->ktij", uh8, val8)
+         + torch.einsum("kcij,ctij->ktij", ul8, vah8))
+    M = M.to(torch.float32).to(F64)                                  # accumulators are fp32
+    Y = _AT @ M @ _AT.t()                                            # (K, T, 2, 2)
+    y = Y.reshape(K, th, tw, 2, 2).permute(0, 1, 3, 2, 4).reshape(1, K, th * 2, tw * 2)
+    return y[:, :, :H, :W]
+
+
 def quant_act(x, scheme):
     """value the NEXT consumer sees for an activation stored in `scheme`'s format"""
     x = x.to(F64)
@@ -58,8 +103,10 @@ def quant_act(x, scheme):
         return ah + rn16(al)
     if scheme == "h2f8" or scheme.startswith("mix") or scheme.startswith("cal"):
         return ah + e5m2(al * 1024.0) / 1024.0      # (cal: only used for the non-tcgen05 consumers; approximation)
-    if scheme == "h2f8v2":                       # candidate: e4m3 bytes with fixed exponents (al * 2^6, hi * 2^-5), saturating
+    if scheme in ("h2f8v2", "h15", "wino"):     # e4m3 bytes with fixed exponents (al * 2^6, hi * 2^-5), saturating
         return ah + e4m3(al * 64.0) / 64.0
+    if scheme == "h15q":                         # e2m1 residual: al * 2^9 puts |al| <= 2^-11 |x| (|x| ~ 2^10) at ~1..6
+        return ah + e2m1(al * 512.0) / 512.0
     if scheme in ("h2f8e4", "h2f8e4b"):          # e4m3 residual with a static 2^9 scale (full precision for 2^-4 <= |x| < 2^11)
         return ah + e4m3(al * 512.0) / 512.0
     if scheme == "h2f8c":           # e5m2 residual, e4m3 copy of hi
@@ -135,6 +182,16 @@ def make_conv(scheme):
             y = cv(ah, wh) + cv(ah, wll) + cv(all_, wh)
         elif scheme == "h2f8v2":
             y = cv(ah, wh) + cv(e4m3(al * 64.0), e4m3(wh / 64.0)) + cv(e4m3(ah / 32.0), e4m3(wl * 32.0))
+        elif scheme == "h15":
+            y = cv(ah, wh) + cv(e4m3(al * 64.0), e4m3(wh / 64.0))
+        elif scheme == "h15q":
+            # 4-bit planes: al * 2^9, ah * 2^-8 (|x| up to ~1500 -> ~6), wh * 2^-12, wl * 2^5 (|wl| <= 4 at the 2^14 scale -> <= 6 after /... )
+            y = cv(ah, wh) + cv(e2m1(al * 512.0), e2m1(wh / 4096.0)) * 8.0 + cv(e2m1(ah / 256.0), e2m1(wl)) * 256.0
+        elif scheme == "wino":
+            if w.shape[2:] == (3, 3) and tuple(dilation) == (1, 1) and tuple(pad) == (1, 1) and tuple(stride) == (1, 1):
+                y = winograd_hf8(quant_act(xt, "h2f8v2"), ws)
+            else:
+                y = cv(ah, wh) + cv(e4m3(al * 64.0), e4m3(wh / 64.0)) + cv(e4m3(ah / 32.0), e4m3(wl * 32.0))
         elif scheme in ("h2f8", "h2f8e4", "h2f8e4b", "h2f8c"):
             if scheme == "h2f8":
                 al8 = e5m2(al * 1024.0)
