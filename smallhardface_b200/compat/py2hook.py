@@ -68,6 +68,99 @@ def transform_source(src: str, filename: str = "<src>") -> str:
     return s
 
 
+# ---- py2 list comprehensions leak their loop variable into the enclosing scope (lib/utils/blob.py:21-23 relies on it) ----
+import ast
+
+
+class _ScopeNodes(ast.NodeVisitor):
+    """Nodes of ONE scope: does not descend into nested functions, lambdas or classes."""
+
+    def __init__(self):
+        self.listcomps, self.loads = [], []
+
+    def visit_FunctionDef(self, node):
+        pass
+    visit_AsyncFunctionDef = visit_Lambda = visit_ClassDef = visit_FunctionDef
+
+    def visit_ListComp(self, node):
+        self.listcomps.append(node)
+        self.generic_visit(node)
+
+    def visit_Name(self, node):
+        if isinstance(node.ctx, ast.Load):
+            self.loads.append(node)
+
+
+def _leak_listcomp_targets(tree):
+    """For every list comprehension in a function (or module) body whose loop variable is ALSO read elsewhere in that scope,
+    reproduce Python 2's behaviour: the variable stays bound to its last value after the statement.  The comprehension
+    gets a always-true filter ``[(__py2leak_x := x)]`` (PEP 572: the walrus target binds in the containing scope) and the
+    enclosing statement is followed by ``try: x = __py2leak_x / except NameError: pass``."""
+    scopes = [tree] + [n for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef))]
+    for scope in scopes:
+        def process(stmts):
+            out = []
+            for st in stmts:
+                leaked = []
+                if isinstance(st, (ast.FunctionDef, ast.AsyncFunctionDef, ast.ClassDef)):
+                    out.append(st)
+                    continue
+                v = _ScopeNodes()
+                v.visit(st)
+                # compound statements: their nested bodies are handled recursively; only patch what is left at this level
+                for field in ("body", "orelse", "finalbody"):
+                    if isinstance(getattr(st, field, None), list) and getattr(st, field) and isinstance(getattr(st, field)[0], ast.stmt):
+                        setattr(st, field, process(getattr(st, field)))
+                for h in getattr(st, "handlers", []) or []:
+                    h.body = process(h.body)
+                nested = set()
+                for field in ("body", "orelse", "finalbody"):
+                    for sub in (getattr(st, field, None) or []):
+                        if isinstance(sub, ast.stmt):
+                            nested.update(id(n) for n in ast.walk(sub))
+                for h in getattr(st, "handlers", []) or []:
+                    for sub in h.body:
+                        nested.update(id(n) for n in ast.walk(sub))
+                for lc in v.listcomps:
+                    if id(lc) in nested:
+                        continue
+                    inside = {id(n) for n in ast.walk(lc)}
+                    for gen in lc.generators:
+                        if not isinstance(gen.target, ast.Name):
+                            continue
+                        name = gen.target.id
+                        if name.startswith("__py2leak_") or name not in scope_loads_outside(name, inside):
+                            continue
+                        tmp = "__py2leak_" + name
+                        gen.ifs.append(ast.List(elts=[ast.NamedExpr(target=ast.Name(id=tmp, ctx=ast.Store()),
+                                                                    value=ast.Name(id=name, ctx=ast.Load()))], ctx=ast.Load()))
+                        leaked.append((name, tmp))
+                out.append(st)
+                for name, tmp in leaked:
+                    out.append(ast.Try(body=[ast.Assign(targets=[ast.Name(id=name, ctx=ast.Store())],
+                                                        value=ast.Name(id=tmp, ctx=ast.Load()))],
+                                       handlers=[ast.ExceptHandler(type=ast.Name(id="NameError", ctx=ast.Load()), name=None,
+                                                                   body=[ast.Pass()])], orelse=[], finalbody=[]))
+            return out
+
+        sv = _ScopeNodes()
+        for st in scope.body:
+            sv.visit(st)
+
+        def scope_loads_outside(name, inside, _loads=sv.loads):
+            return {n.id for n in _loads if n.id == name and id(n) not in inside}
+
+        scope.body = process(scope.body)
+    ast.fix_missing_locations(tree)
+    return tree
+
+
+def compile_py2(src: str, filename: str, optimize: int = -1):
+    """Source text of a Python 2 file -> code object (text-level transform, then the comprehension-leak AST pass)."""
+    tree = ast.parse(transform_source(src, filename), filename)
+    return compile(_leak_listcomp_targets(tree), filename, "exec", dont_inherit=True, optimize=optimize)
+
+
 class _Loader(importlib.abc.SourceLoader):
     def __init__(self, fullname, path):
         self.fullname, self.path = fullname, path
@@ -81,7 +174,7 @@ class _Loader(importlib.abc.SourceLoader):
 
     def source_to_code(self, data, path, *, _optimize=-1):
         text = data.decode("utf-8") if isinstance(data, bytes) else data
-        return compile(transform_source(text, path), path, "exec", dont_inherit=True, optimize=_optimize)
+        return compile_py2(text, path, _optimize)
 
     # never write / trust .pyc files of transformed sources
     def path_stats(self, path):

@@ -35,7 +35,7 @@ def main():
     script = os.path.join(ref, "train_test.py")
     with open(script) as f:
         src = f.read()
-    code = compile(py2hook.transform_source(src, script), script, "exec")
+    code = py2hook.compile_py2(src, script)
     sys.argv = [script] + rest
     glb = {"__name__": "__main__", "__file__": script, "__builtins__": __builtins__}
     exec(code, glb)
