@@ -153,12 +153,14 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
     }
     uint8_t* stg = stage_s + warp * 4096;
     const int qy = y0 + warp * 4;
+    __half* base = p.out + (((size_t)img * p.H + qy) * p.W + x0) * (size_t)64;
+    const uint32_t pitch = (uint32_t)p.W * 64u;
     auto dst = [&](int row) -> __half* {
-      const int yy = qy + (row >> 3), xx = x0 + (row & 7);
-      return (yy < p.H && xx < p.W) ? p.out + (((size_t)img * p.H + yy) * p.W + xx) * (size_t)64 : nullptr;
+      const int dy = row >> 3, dx = row & 7;
+      return (qy + dy < p.H && x0 + dx < p.W) ? base + ((uint32_t)dy * pitch + (uint32_t)dx * 64u) : nullptr;
     };
-    store_plane<64>(stg, lane, true, lane, 32, v, 0, p.out_fmt, 0, (size_t)p.plane_elems, dst);
-    store_plane<64>(stg, lane, true, lane, 32, v, 1, p.out_fmt, 0, (size_t)p.plane_elems, dst);
+    store_plane<64>(stg, lane, v, 0, p.out_fmt, 0, (size_t)p.plane_elems, dst);
+    store_plane<64>(stg, lane, v, 1, p.out_fmt, 0, (size_t)p.plane_elems, dst);
   }
   range_guard_commit(p.guard, gmax);
   tc_fence_before();

@@ -344,7 +344,6 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < p.H && x < p.W);
       const int n0 = nt * BN;
-      const bool pool_writer = p.pool_out && inside && !(lane & 9);        // lane bits 0 (x) and 3 (y) clear: window origin
       if ((p.probe & 3) == 2) continue;
 #pragma unroll
       for (int c = 0; c < kCols; ++c) {
@@ -357,37 +356,27 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       uint8_t* stg = stage_s + w * 4096;
       const int c_first = n0 + col0;
+      const int qy = y0 + quad * 4;                         // this warp's 4 x 8 pixel patch starts at (qy, x0)
       if (p.out && (p.probe & 3) != 1) {
-        const int qy = y0 + quad * 4;                       // this warp's 4 x 8 pixel patch
+        // row pointers = one 64-bit base per tile + 32-bit offsets (W * ctot < 2^31 elements is checked on the host)
+        __half* base = p.out + (((size_t)img * p.H + qy) * p.W + x0) * (size_t)p.ctot;
+        const uint32_t pitch = (uint32_t)p.W * (uint32_t)p.ctot, ct = (uint32_t)p.ctot;
         auto dst = [&](int row) -> __half* {
-          const int yy = qy + (row >> 3), xx = x0 + (row & 7);
-          return (yy < p.H && xx < p.W) ? p.out + (((size_t)img * p.H + yy) * p.W + xx) * (size_t)p.ctot : nullptr;
+          const int dy = row >> 3, dx = row & 7;
+          return (qy + dy < p.H && x0 + dx < p.W) ? base + ((uint32_t)dy * pitch + (uint32_t)dx * ct) : nullptr;
         };
-        store_plane<kCols>(stg, lane, true, lane, 32, acc, 0, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
-        store_plane<kCols>(stg, lane, true, lane, 32, acc, 1, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
+        store_plane<kCols>(stg, lane, acc, 0, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
+        store_plane<kCols>(stg, lane, acc, 1, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
       }
-      if (p.pool_out) {                                     // warp-uniform branch: all lanes take part in the shuffles
-#pragma unroll
-        for (int c = 0; c < kCols; ++c) {
-          float q = inside ? acc[c] : -3.402823466e38f;
-          q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
-          q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 8));
-          acc[c] = q;
-        }
-        if ((p.probe & 3) != 1) {
-          const int qy = y0 + quad * 4;
-          const int ph2 = p.H >> 1, pw2 = p.W >> 1;
-          auto dst = [&](int row) -> __half* {              // row = pooled pixel (2 rows x 4 columns per warp)
-            const int yy = qy + ((row >> 2) << 1), xx = x0 + ((row & 3) << 1);
-            return (yy < p.H && xx < p.W)
-                       ? p.pool_out + (((size_t)img * ph2 + (yy >> 1)) * pw2 + (xx >> 1)) * (size_t)p.pool_ctot
-                       : nullptr;
-          };
-          store_plane<kCols>(stg, lane, pool_writer, lane, 8, acc, 0, p.out_fmt, p.pool_coffset + c_first,
-                             (size_t)p.pool_plane_elems, dst);
-          store_plane<kCols>(stg, lane, pool_writer, lane, 8, acc, 1, p.out_fmt, p.pool_coffset + c_first,
-                             (size_t)p.pool_plane_elems, dst);
-        }
+      if (p.pool_out && (p.probe & 3) != 1) {               // warp-uniform branch: all lanes take part in the shuffles
+        const int ph2 = p.H >> 1, pw2 = p.W >> 1;
+        __half* base = p.pool_out + (((size_t)img * ph2 + (qy >> 1)) * pw2 + (x0 >> 1)) * (size_t)p.pool_ctot;
+        const uint32_t pitch = (uint32_t)pw2 * (uint32_t)p.pool_ctot, ct = (uint32_t)p.pool_ctot;
+        auto dst = [&](int row) -> __half* {                // row = pooled pixel (2 rows x 4 columns per warp)
+          const int dy = row >> 2, dx = row & 3;
+          return (qy + 2 * dy < p.H && x0 + 2 * dx < p.W) ? base + ((uint32_t)dy * pitch + (uint32_t)dx * ct) : nullptr;
+        };
+        store_pooled<kCols>(stg, lane, acc, p.out_fmt, p.pool_coffset + c_first, (size_t)p.pool_plane_elems, dst);
       }
     }
     range_guard_commit(p.guard, gmax);
@@ -470,6 +459,9 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
               "shf_conv_igemm: bad destination channel window [%d,%d) of %d", out_channel_offset,
               out_channel_offset + cout, out_channels_total);
   SHF_REQUIRE(batch >= 1 && H >= 1 && W >= 1 && dilation >= 1 && dilation <= 4, "shf_conv_igemm: bad geometry");
+  SHF_REQUIRE((long long)W * out_channels_total < (1ll << 29) && (long long)W * pool_channels_total < (1ll << 29),
+              "shf_conv_igemm: a row of %d pixels x %d channels overflows the epilogue's 32-bit in-tile offsets", W,
+              out_channels_total);
   const int bn = (cout % 128 == 0) ? 128 : 64;
   StreamParams p;
   p.H = H; p.W = W; p.batch = batch;

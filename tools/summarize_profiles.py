@@ -79,9 +79,37 @@ if out:
         f.write("Commands: `ncu --set full --clock-control none --import-source on -k regex:conv_stream -s 2 -c 1 -o gpurun_out/<name> "
                 "python tools/ncu_one.py 8 <Cin> <Cout> <H> <W> 3 1 <fmt>` on shapes of the 2048-px level (conv4_2: 512->512 at 256x256; "
                 "conv2_2: 128->128 at 1024x1024; conv1_2: 64->64 at 2048x2048; fmt 0 = split fp16, 1 = fp16 + fp8) and the same for "
-                "`conv1_tc` (3->64 at 2048x2048).  Read: tensor pipe 94 % / 91 % active on conv4_2 (h2 / hf8), 86 % on conv2_2 hf8, "
-                "64 % on the 64-channel conv1_2 (shared-memory operand reads: l1tex 80 %); DRAM traffic = algorithmic bytes.\n\n")
+                "`conv1_tc` (3->64 at 2048x2048; captured inside tools/level_conv_only.py) and the post-processing kernels (first five "
+                "launches of smoke()).\n\n")
         f.write("| capture | " + " | ".join(k.replace("_", "\\_") for k in KEYS) + " |\n|---|" + "---:|" * len(KEYS) + "\n")
         for rep, d in out:
             f.write("| %s | " % rep + " | ".join("%s %s" % (d.get(k, ("", ""))[0], d.get(k, ("", ""))[1]) for k in KEYS) + " |\n")
     print(open(os.path.join(prof, "%s_ncu_full.md" % tag)).read()[:3000])
+
+# ---- BASELINE configs[1]: per-conv ncu metrics of one whole 2048x2048 level (tools/level_conv_only.py 2048 1 under ncu) ----
+lv = os.path.join(go, "%s_level2048_ncu.csv" % tag)
+if os.path.exists(lv):
+    L = launches(lv)
+    names = ["conv1_2+pool", "conv2_1", "conv2_2+pool", "conv3_1", "conv3_2", "conv3_3+pool", "conv4_1", "conv4_2", "conv4_3+pool",
+             "conv5_1", "conv5_2", "conv5_3", "conv5_256", "conv4_256", "conv4_fuse_final", "conv4_fuse_final_dim_red", "head_1",
+             "head_2", "head_4"]
+    n = len(names)
+    if len(L) == 4 * n:                             # per format: one warm-up pass + one timed pass
+        pipe = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
+        with open(os.path.join(prof, "%s_level2048_ncu.md" % tag), "w") as f:
+            f.write("# %s -- every tcgen05 conv launch of one 2048x2048 pyramid level under ncu (BASELINE configs[1])\n\n" % tag)
+            f.write("Command: `ncu --metrics gpu__time_duration.sum,%s,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+                    "-k regex:conv_stream --csv python tools/level_conv_only.py 2048 1` (dilated-head net, batch 1; second pass of each "
+                    "operand format).  Durations are cold-cache / serialised; the CUDA-event table of the same launches is "
+                    "`%s_level2048_conv_only.txt`.\n\n" % (pipe, tag))
+            for title, off in (("h2 (split fp16, 3 MMAs per 16 channels)", n), ("hf8 (f16 + f8 correction, 2 MMAs per 16 channels)", 3 * n)):
+                f.write("## operand format %s\n\n| layer | us | tensor pipe active %% | DRAM MB read | DRAM MB written |\n|---|---:|---:|---:|---:|\n" % title)
+                tot = 0.0
+                for name, d in zip(names, L[off:off + n]):
+                    tot += d["gpu__time_duration.sum"]
+                    f.write("| %s | %.1f | %.1f | %.1f | %.1f |\n" % (name, d["gpu__time_duration.sum"] / 1e3, d.get(pipe, float("nan")),
+                                                                    d.get("dram__bytes_read.sum", 0) / 1e6, d.get("dram__bytes_write.sum", 0) / 1e6))
+                f.write("| **all 19** | **%.1f** | | | |\n\n" % (tot / 1e3))
+        print(open(os.path.join(prof, "%s_level2048_ncu.md" % tag)).read())
+    else:
+        print("level2048 csv: %d launches, expected %d" % (len(L), 4 * n))
