@@ -338,3 +338,35 @@ def test_detection_writer_byte_exact_vs_reference_golden(tmp_path):
     write_detections(["/data/a/im0.png"], [boxes[2]], str(tmp_path / "g"), extension="png", strip_leading_slash=True)
     txt = open(os.path.join(str(tmp_path / "g"), "data", "a", "im0.txt")).read().splitlines()
     assert txt[0] == "/data/a/im0.png" and txt[1] == "3" and len(txt) == 5 and txt[2].endswith(" ")
+
+
+def test_py2_hook_reproduces_list_comprehension_variable_leak():
+    """Python 2 leaves a list comprehension's loop variable bound in the enclosing scope; `lib/utils/blob.py:21-23` reads
+    `im.shape[2]` after `[im.shape for im in ims]`.  The hook reproduces that (and print statements, xrange, has_key ...)
+    without touching the files on disk."""
+    from smallhardface_b200.compat import py2hook
+    src = '''
+def shapes(ims):
+    m = max([im[0] for im in ims])
+    return m, im[1]
+def untouched(xs):
+    ys = [x + 1 for x in xs]
+    return ys
+def nested(xs):
+    if xs:
+        zs = [q * 2 for q in xs]
+        return q
+    return None
+d = {1: 2}
+flag = d.has_key(1)
+total = 0
+for i in xrange(3):
+    total += i
+print >>__import__("sys").stderr, "py2 print", total
+'''
+    ns = {}
+    exec(py2hook.compile_py2(src, "<py2>"), ns)
+    assert ns["shapes"]([(1, 10), (5, 20), (3, 30)]) == (5, 30)
+    assert ns["untouched"]([1, 2]) == [2, 3]
+    assert ns["nested"]([1, 5]) == 5 and ns["nested"]([]) is None
+    assert ns["flag"] is True and ns["total"] == 3
