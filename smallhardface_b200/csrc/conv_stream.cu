@@ -345,14 +345,19 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool inside = (y < p.H && x < p.W);
       const int n0 = nt * BN;
       if ((p.probe & 3) == 2) continue;
+      // When only the pooled map is written (conv1_2, conv2_2, conv3_3) bias + ReLU + guard run AFTER the pooling, on the
+      // quarter of the values each lane keeps: max commutes exactly with x -> relu(x * scale + bias), scale = 2^-k > 0.
+      const bool post_pool = p.pool_out && !p.out;
+      if (!post_pool) {
 #pragma unroll
-      for (int c = 0; c < kCols; ++c) {
-        acc[c] = fmaf(acc[c], scale, bias_t[col0 + c]);
-        if (p.relu) acc[c] = fmaxf(acc[c], 0.f);
-      }
-      if (p.guard && inside) {
+        for (int c = 0; c < kCols; ++c) {
+          acc[c] = fmaf(acc[c], scale, bias_t[col0 + c]);
+          if (p.relu) acc[c] = fmaxf(acc[c], 0.f);
+        }
+        if (p.guard && inside) {
 #pragma unroll
-        for (int c = 0; c < kCols; ++c) gmax = fmaxf(gmax, fabsf(acc[c]));
+          for (int c = 0; c < kCols; ++c) gmax = fmaxf(gmax, fabsf(acc[c]));
+        }
       }
       uint8_t* stg = stage_s + w * 4096;
       const int c_first = n0 + col0;
@@ -376,7 +381,20 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int dy = row >> 2, dx = row & 3;
           return (qy + 2 * dy < p.H && x0 + 2 * dx < p.W) ? base + ((uint32_t)dy * pitch + (uint32_t)dx * ct) : nullptr;
         };
-        store_pooled<kCols>(stg, lane, acc, p.out_fmt, p.pool_coffset + c_first, (size_t)p.pool_plane_elems, dst);
+        if (post_pool) {
+          const float* bias_w = bias_t + col0;
+          const bool relu = p.relu != 0, guard = p.guard != nullptr && inside;
+          store_pooled<kCols>(stg, lane, acc, p.out_fmt, p.pool_coffset + c_first, (size_t)p.pool_plane_elems, dst,
+                              [&](float x, int ch) {
+                                float y = fmaf(x, scale, bias_w[ch]);
+                                if (relu) y = fmaxf(y, 0.f);
+                                if (guard) gmax = fmaxf(gmax, fabsf(y));
+                                return y;
+                              });
+        } else {
+          store_pooled<kCols>(stg, lane, acc, p.out_fmt, p.pool_coffset + c_first, (size_t)p.pool_plane_elems, dst,
+                              [](float x, int) { return x; });
+        }
       }
     }
     range_guard_commit(p.guard, gmax);

@@ -131,8 +131,12 @@ SHF_DEVICE void store_plane(uint8_t* stg, int lane, const float (&v)[KC], int pl
 // and staging stores then run on KC / 4 values in all 32 lanes instead of KC values in the 8 window-origin lanes (the
 // other 24 predicated off but still issued).  H and W are even and tiles are 16 x 8 aligned, so a window is never cut by
 // the image border.  v is consumed (overwritten).
-template <int KC, typename DstFn>
-SHF_DEVICE void store_pooled(uint8_t* stg, int lane, float (&v)[KC], int fmt, int c_first, size_t plane_elems, DstFn dst_px) {
+// post(value, channel) is applied to the KC / 4 window maxima this lane ends up owning (channel = index within the warp's
+// KC): callers whose un-pooled tensor is not written pass the bias + ReLU there -- max pooling commutes exactly with a
+// non-decreasing map, so it runs on a quarter of the values.
+template <int KC, typename DstFn, typename PostFn>
+SHF_DEVICE void store_pooled(uint8_t* stg, int lane, float (&v)[KC], int fmt, int c_first, size_t plane_elems, DstFn dst_px,
+                             PostFn post) {
   using RS = RowStore<KC>;
   constexpr int H2c = KC / 2, Q = KC / 4;                    // channels kept after the x- / y-exchange
   const bool bx = lane & 1, by = lane & 8;
@@ -150,6 +154,8 @@ SHF_DEVICE void store_pooled(uint8_t* stg, int lane, float (&v)[KC], int fmt, in
     v[c] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 8));
   }
   const int cs = (bx ? H2c : 0) + (by ? Q : 0);              // first channel (within the warp's KC) this lane now owns
+#pragma unroll
+  for (int c = 0; c < Q; ++c) v[c] = post(v[c], cs + c);
   const int prow = ((lane >> 4) << 2) | ((lane >> 1) & 3);   // pooled pixel: (y >> 1) * 4 + (x >> 1)
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
