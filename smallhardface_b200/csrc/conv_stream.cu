@@ -66,7 +66,16 @@ struct StreamParams {
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-template <int BN, int CTAS>
+#ifdef SHF_PROBES
+constexpr bool kProbes = true;
+#else
+constexpr bool kProbes = false;               // product builds: the timing probes are compiled out of the hot loops
+#endif
+
+// FMT = operand format of the activations read AND of the packed weights (SHF_FMT_*): a template parameter so that the
+// MMA-issuing thread's loop carries no format / probe / residency tests (r02: ncu showed that thread, at ~110 SASS
+// instructions and 550 cycles per 8-MMA weight stage, pacing every layer -- the N = 64 ones at half the tensor rate).
+template <int BN, int CTAS, int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const StreamParams p) {
@@ -167,7 +176,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         decode_tile(t, nt, x0, y0, img);
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
           mbar_wait(empty_a(sa), pha ^ 1);
-          if (p.probe & 4) {                     // timing probe: no activation loads at all
+          if (kProbes && (p.probe & 4)) {       // timing probe: no activation loads at all
             if (rank == 0) mbar_arrive(full_a(sa));
           } else if (CTAS == 2) {
             if (rank == 0) mbar_arrive_expect_tx(full_a(sa), 2 * p.a_tx);
@@ -199,83 +208,129 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tap_dx = (uint32_t)p.dil * 128u;                              // bytes to the next tap column
     const uint32_t tap_dy = (uint32_t)(p.dil * p.xw) * 128u - (uint32_t)ktaps * tap_dx;   // ... and on to the next tap row
     const bool issuer = elect_one();          // the one lane that talks to the tensor core
-    int sa = 0, sb = 0, gp = 0;
-    uint32_t pha = 0, phb = 0;
-    for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
-      for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
-        const int set = gp & 1;
-        const uint32_t d_main = (uint32_t)set * kSetCols;
-        mbar_wait(acc_empty(set), ((gp >> 1) & 1) ^ 1);           // drained by the epilogue warps (of both CTAs)
-        tc_fence_after();
-        const int c_begin = ph * p.chunks_per_phase;
-        const int c_end = min(c_begin + p.chunks_per_phase, p.cin_chunks);
-        uint32_t opened = 0;                                      // 0 until the set has been overwritten once
-        for (int cc = c_begin; cc < c_end; ++cc) {
-          mbar_wait(full_a(sa), pha);
-          const uint32_t a_base = a_stage(sa);
-          uint32_t a_off = 0;
-          int s = 0;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            mbar_wait(full_b(sb), p.b_resident ? 0u : phb);       // resident: filled once (phase 0)
+    // loop-invariant parameters in registers (the asm volatile MMAs would otherwise force constant-bank reloads per stage)
+    const int taps = p.taps, nb = p.nb, na = p.na, cin_chunks = p.cin_chunks, cpp = p.chunks_per_phase;
+    const uint32_t a_bytes = (uint32_t)p.a_bytes, b_bytes = (uint32_t)p.b_bytes;
+    const uint32_t b_ring = smem_base + (uint32_t)na * a_bytes;
+    const bool skip_mma = kProbes && (p.probe & 8);          // timing probe: no MMAs, only the barrier traffic
+    // the 8 (hf8) or 12 (h2) MMAs of one weight stage = one tap of one 64-channel chunk
+    auto issue_stage = [&](uint32_t d_main, uint32_t a_lo32, uint32_t b_lo32, uint32_t opened) {
+      if (skip_mma) return;
+      if (FMT == SHF_FMT_HF8) {
+        // hi*hi as one f16 MMA, the first-order correction [al8 | ah8] x [wh8 | wl8] as one f8 MMA over the
+        // same 32 bytes of K per operand row (plane 1 of either stage), both into the same accumulator
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) {
+          if (CTAS == 2) {
+            umma2_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+            umma2_f8(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+          } else {
+            umma1_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+            umma1_f8(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
+          }
+          opened = 1u;
+          a_lo32 += 2; b_lo32 += 2;
+        }
+      } else if (CTAS == 2) {
+        // the pair's weight stage is split by output channel, so hi and lo rows are separate N = BN operands:
+        //   main += A_hi x B_hi ;  cross += A_hi x B_lo ;  cross += A_lo x B_hi
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) {
+          umma2_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
+          umma2_f16(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
+          umma2_f16(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+          opened = 1u;
+          a_lo32 += 2; b_lo32 += 2;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) {
+          // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
+          umma1_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
+          // cross += A_lo x B_hi
+          umma1_f16(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
+          opened = 1u;
+          a_lo32 += 2; b_lo32 += 2;
+        }
+      }
+    };
+    auto commit = [&](uint32_t bar) { if (CTAS == 2) umma2_commit(bar); else umma_commit(bar); };
+    int sa = 0, gp = 0;
+    uint32_t pha = 0;
+    if (p.b_resident) {
+      // ---- resident weights (conv1_2: one N tile, all taps in the ring): wait for them ONCE, then every halo is one
+      //      single-thread region that issues all of its taps back to back -- no per-tap barrier wait, election or
+      //      ring bookkeeping between the MMAs
+      for (int s2 = 0; s2 < nb; ++s2) mbar_wait(full_b(s2), 0u);
+      tc_fence_after();
+      for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
+        for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
+          const int set = gp & 1;
+          const uint32_t d_main = (uint32_t)set * kSetCols;
+          mbar_wait(acc_empty(set), ((gp >> 1) & 1) ^ 1);
+          const int c_begin = ph * cpp;
+          const int c_end = min(c_begin + cpp, cin_chunks);
+          uint32_t opened = 0;
+          for (int cc = c_begin; cc < c_end; ++cc) {
+            mbar_wait(full_a(sa), pha);
             tc_fence_after();
-            uint32_t a_lo32 = (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo;
-            uint32_t b_lo32 = ((b_stage(sb) & 0x3FFFFu) >> 4) | lbo;
-            if (issuer) {                       // ONE single-thread region per weight stage: 8 or 12 MMAs + the stage release
-              if (p.probe & 8) {                 // timing probe: no MMAs, only the barrier traffic
-              } else if (p.in_fmt == SHF_FMT_HF8) {
-                // hi*hi as one f16 MMA, the first-order correction [al8 | ah8] x [wh8 | wl8] as one f8 MMA over the
-                // same 32 bytes of K per operand row (plane 1 of either stage), both into the same accumulator
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) {
-                  if (CTAS == 2) {
-                    umma2_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                    umma2_f8(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
-                  } else {
-                    umma1_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                    umma1_f8(d_main, a_lo32 + a_plane16, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_f8, 1u);
-                  }
-                  opened = 1u;
-                  a_lo32 += 2; b_lo32 += 2;
-                }
-              } else if (CTAS == 2) {
-                // the pair's weight stage is split by output channel, so hi and lo rows are separate N = BN operands:
-                //   main += A_hi x B_hi ;  cross += A_hi x B_lo ;  cross += A_lo x B_hi
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) {
-                  umma2_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_half, opened);
-                  umma2_f16(d_main + BN, a_lo32, a_hi32, b_lo32 + b_plane16, b_hi32, idesc_half, opened);
-                  umma2_f16(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
-                  opened = 1u;
-                  a_lo32 += 2; b_lo32 += 2;
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) {
-                  // [main | cross] += A_hi x [B_hi ; B_lo]   (first MMA of a phase overwrites both halves)
-                  umma1_f16(d_main, a_lo32, a_hi32, b_lo32, b_hi32, idesc_wide, opened);
-                  // cross += A_lo x B_hi
-                  umma1_f16(d_main + BN, a_lo32 + a_plane16, a_hi32, b_lo32, b_hi32, idesc_half, 1u);
-                  opened = 1u;
-                  a_lo32 += 2; b_lo32 += 2;
-                }
+            if (issuer) {
+              const uint32_t a_base = smem_base + (uint32_t)sa * a_bytes;
+              uint32_t a_off = 0, b_addr = b_ring + (uint32_t)(cc * taps) * b_bytes;
+              int s = 0;
+              for (int tap = 0; tap < taps; ++tap) {
+                issue_stage(d_main, (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo, ((b_addr & 0x3FFFFu) >> 4) | lbo, opened);
+                opened = 1u;
+                b_addr += b_bytes;
+                a_off += tap_dx;
+                if (++s == ktaps) { s = 0; a_off += tap_dy; }
               }
-              if (!p.b_resident) {
-                if (CTAS == 2) umma2_commit(empty_b(sb)); else umma_commit(empty_b(sb));
-              }
-              if (tap == p.taps - 1) {          // last tap of this halo: hand the A stage back as well
-                if (CTAS == 2) umma2_commit(empty_a(sa)); else umma_commit(empty_a(sa));
-                if (cc == c_end - 1) {          // ... and, after the phase's last chunk, publish the accumulator set
-                  if (CTAS == 2) umma2_commit(acc_full(set)); else umma_commit(acc_full(set));
-                }
-              }
+              commit(empty_a(sa));
+              if (cc == c_end - 1) commit(acc_full(set));
             }
             __syncwarp();
             opened = 1u;
-            if (++sb == p.nb) { sb = 0; phb ^= 1; }
-            a_off += tap_dx;
-            if (++s == ktaps) { s = 0; a_off += tap_dy; }
+            if (++sa == na) { sa = 0; pha ^= 1; }
           }
-          if (++sa == p.na) { sa = 0; pha ^= 1; }
+        }
+      }
+    } else {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
+        for (int ph = 0; ph < phases_per_tile; ++ph, ++gp) {
+          const int set = gp & 1;
+          const uint32_t d_main = (uint32_t)set * kSetCols;
+          mbar_wait(acc_empty(set), ((gp >> 1) & 1) ^ 1);           // drained by the epilogue warps (of both CTAs)
+          tc_fence_after();
+          const int c_begin = ph * cpp;
+          const int c_end = min(c_begin + cpp, cin_chunks);
+          uint32_t opened = 0;                                      // 0 until the set has been overwritten once
+          for (int cc = c_begin; cc < c_end; ++cc) {
+            mbar_wait(full_a(sa), pha);
+            const uint32_t a_base = smem_base + (uint32_t)sa * a_bytes;
+            uint32_t a_off = 0;
+            int s = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(full_b(sb), phb);
+              tc_fence_after();
+              if (issuer) {                       // ONE single-thread region per weight stage: 8 or 12 MMAs + the stage release
+                issue_stage(d_main, (((a_base + a_off) & 0x3FFFFu) >> 4) | lbo,
+                            (((b_ring + (uint32_t)sb * b_bytes) & 0x3FFFFu) >> 4) | lbo, opened);
+                commit(empty_b(sb));
+                if (tap == taps - 1) {            // last tap of this halo: hand the A stage back as well
+                  commit(empty_a(sa));
+                  if (cc == c_end - 1) commit(acc_full(set));       // ... and, after the phase's last chunk, the accumulators
+                }
+              }
+              __syncwarp();
+              opened = 1u;
+              if (++sb == nb) { sb = 0; phb ^= 1; }
+              a_off += tap_dx;
+              if (++s == ktaps) { s = 0; a_off += tap_dy; }
+            }
+            if (++sa == na) { sa = 0; pha ^= 1; }
+          }
         }
       }
     }
@@ -312,7 +367,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_wait(acc_full(set), (gp >> 1) & 1);
         tc_fence_after();
         const uint32_t base = lane_addr + (uint32_t)set * kSetCols;
-        if (p.in_fmt == SHF_FMT_HF8) {
+        if (FMT == SHF_FMT_HF8) {
 #pragma unroll
           for (int c0 = 0; c0 < kCols; c0 += 32) {
             uint32_t mq[32];
@@ -344,7 +399,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool inside = (y < p.H && x < p.W);
       const int n0 = nt * BN;
-      if ((p.probe & 3) == 2) continue;
+      if (kProbes && (p.probe & 3) == 2) continue;
       // When only the pooled map is written (conv1_2, conv2_2, conv3_3) bias + ReLU + guard run AFTER the pooling, on the
       // quarter of the values each lane keeps: max commutes exactly with x -> relu(x * scale + bias), scale = 2^-k > 0.
       const bool post_pool = p.pool_out && !p.out;
@@ -362,7 +417,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint8_t* stg = stage_s + w * 4096;
       const int c_first = n0 + col0;
       const int qy = y0 + quad * 4;                         // this warp's 4 x 8 pixel patch starts at (qy, x0)
-      if (p.out && (p.probe & 3) != 1) {
+      if (p.out && !(kProbes && (p.probe & 3) == 1)) {
         // row pointers = one 64-bit base per tile + 32-bit offsets (W * ctot < 2^31 elements is checked on the host)
         __half* base = p.out + (((size_t)img * p.H + qy) * p.W + x0) * (size_t)p.ctot;
         const uint32_t pitch = (uint32_t)p.W * (uint32_t)p.ctot, ct = (uint32_t)p.ctot;
@@ -373,7 +428,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         store_plane<kCols>(stg, lane, acc, 0, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
         store_plane<kCols>(stg, lane, acc, 1, p.out_fmt, p.cout_offset + c_first, (size_t)p.plane_elems, dst);
       }
-      if (p.pool_out && (p.probe & 3) != 1) {               // warp-uniform branch: all lanes take part in the shuffles
+      if (p.pool_out && !(kProbes && (p.probe & 3) == 1)) {  // warp-uniform branch: all lanes take part in the shuffles
         const int ph2 = p.H >> 1, pw2 = p.W >> 1;
         __half* base = p.pool_out + (((size_t)img * ph2 + (qy >> 1)) * pw2 + (x0 >> 1)) * (size_t)p.pool_ctot;
         const uint32_t pitch = (uint32_t)pw2 * (uint32_t)p.pool_ctot, ct = (uint32_t)p.pool_ctot;
@@ -407,18 +462,18 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, int FMT>
 int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
                   cudaStream_t stream) {
   static bool attr[64] = {};                   // function attributes are per device
   int dev = 0;
   SHF_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr[dev]) {
-    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   if (CTAS == 1) {
-    conv_stream_kernel<BN, CTAS><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    conv_stream_kernel<BN, CTAS, FMT><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -432,7 +487,7 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamPara
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS>, ta, tb, p));
+    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS, FMT>, ta, tb, p));
   }
   SHF_LAUNCH_CHECK();
   return 0;
@@ -544,9 +599,17 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   const int groups = sm_count() / ctas;
   const int grid = (p.total_tiles < groups ? p.total_tiles : groups) * ctas;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (ctas == 2)
-    return bn == 128 ? launch_stream<128, 2>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64, 2>(ta, tb, p, smem_bytes, grid, st);
-  return bn == 128 ? launch_stream<128, 1>(ta, tb, p, smem_bytes, grid, st) : launch_stream<64, 1>(ta, tb, p, smem_bytes, grid, st);
+  const bool f8 = in_format == SHF_FMT_HF8;
+  if (ctas == 2) {
+    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
+                             : launch_stream<128, 2, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
+    return f8 ? launch_stream<64, 2, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
+              : launch_stream<64, 2, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
+  }
+  if (bn == 128) return f8 ? launch_stream<128, 1, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
+                           : launch_stream<128, 1, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
+  return f8 ? launch_stream<64, 1, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
+            : launch_stream<64, 1, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
 }
 
 // ---- C ABI (include/shf_b200.h) ---------------------------------------------------------------------------------
