@@ -497,8 +497,8 @@ def run_ours(args):
                         "shf_bbox_vote_host; one CUDA graph per level shape",
                 "gpu_launches": int(plug_launches),
                 "breakdown_ms_per_image": {
-                    "input_blob_assign (im_info and first-time copies)": 1e3 * pr.get("assign_s", 0.0) / nimg,
-                    "host copy into the page-locked blob pipelined with its H2D, graph launch, D2H enqueue": 1e3 * pr.get("enqueue_s", 0.0) / nimg,
+                    "input_blob_assign (caller array -> page-locked blob)": 1e3 * pr.get("assign_s", 0.0) / nimg,
+                    "enqueue (H2D + graph launch + D2H, async)": 1e3 * pr.get("enqueue_s", 0.0) / nimg,
                     "wait (GPU time the host could not hide)": 1e3 * pr.get("wait_s", 0.0) / nimg,
                     "driver numpy + threshold + vote call": 1e3 * (e2e_s / nimg) - 1e3 * (pr.get("assign_s", 0.0) + pr.get("enqueue_s", 0.0) + pr.get("wait_s", 0.0)) / nimg,
                     "total": 1e3 * e2e_s / nimg}}

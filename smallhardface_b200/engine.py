@@ -698,15 +698,13 @@ class GpuNet:
         return buf["out_boxes"], buf["out_probs"], buf["pack"][:1].view(torch.int32)
 
     # -- plugin path: one CUDA graph per (padded shape, im_info, operand format) ------------------------------
-    def forward_cached(self, data_src: torch.Tensor, im_info, feed=None):
+    def forward_cached(self, data_src: torch.Tensor, im_info):
         """``forward`` for the batch-1 plugin surface: ``data_src`` is the (1,3,H,W) float32 level blob in PAGE-LOCKED host
         memory (or on the device).  The whole forward -- ~25 launches whose arguments depend only on the padded shape,
         ``im_info`` and the operand format -- is captured once into a CUDA graph with its activations in the graph's own
         memory pool and replayed afterwards: one upload + one graph launch per forward instead of a ctypes call and two
         tensor-map encodes per layer.  Returns the device result block ``pack`` (see run_tail) or None (no tail).
-        ``feed(x)``: optional callback that fills the graph's static device input itself (the caffe shim overlaps the copy
-        into page-locked memory with the upload, chunk by chunk); only used when the graph already exists -- otherwise
-        ``data_src`` must hold the data.  Graphs live in an LRU bounded by ``graph_budget_bytes`` / ``graph_max_entries``."""
+        Graphs live in an LRU bounded by ``graph_budget_bytes`` / ``graph_max_entries``."""
         import os
         info = (float(im_info[0]), float(im_info[1]), float(im_info[2]))
         fast = self.use_fast(info[2])
@@ -714,8 +712,6 @@ class GpuNet:
         cache = self.__dict__.setdefault("_graphs", OrderedDict())
         ent = cache.get(key)
         if ent is None:
-            if feed is not None:
-                raise L.ShfError("forward_cached: feed() needs an existing graph (call has_graph first)")
             x = torch.empty(tuple(data_src.shape), dtype=torch.float32, device=self.device)
             x.copy_(data_src, non_blocking=True)
             if os.environ.get("SHF_CUDA_GRAPHS", "1") == "0" or self.profile or self.has_python:
@@ -740,19 +736,11 @@ class GpuNet:
                 cache.popitem(last=False)                     # least recently used: frees its pool
         else:
             cache.move_to_end(key)
-            if feed is not None:
-                feed(ent["x"])
-            else:
-                ent["x"].copy_(data_src, non_blocking=True)
+            ent["x"].copy_(data_src, non_blocking=True)
         ent["graph"].replay()
         self.tensors = ent["tensors"]
         self.launches += ent["launches"]
         return ent["pack"]
-
-    def has_graph(self, shape, im_info) -> bool:
-        info = (float(im_info[0]), float(im_info[1]), float(im_info[2]))
-        key = (tuple(shape), info, self.use_fast(info[2]), tuple(sorted(self.cfg.items())))
-        return key in self.__dict__.get("_graphs", {})
 
     def run_tail_batched(self, nf, im_info, dets, pass_offsets, image_base, passes_total, pass_base, det_cap,
                          det_thresh=0.05):

@@ -177,23 +177,16 @@ class Net(object):
         import torch
         prof = self._prof                                       # bench.py: where a forward's host time goes
         t0 = _now() if prof is not None else 0.0
-        eng = self._engine
-        eng.cfg.update(_hot_path_cfg())
-        fast_path = not (eng.tail is None or eng.has_python or len(self.inputs) != 2)
-        deferred = None                                          # the data array, when its copy is overlapped with the upload
         if kwargs:
             if set(kwargs.keys()) != set(self.inputs):
                 raise Exception("Input blob arguments do not match net inputs.")
             for in_, blob in kwargs.items():
                 if blob.shape[0] != self.blobs[in_].shape[0]:
                     raise Exception("Input is not batch sized")
-            for in_, blob in kwargs.items():
-                if (fast_path and in_ == self.inputs[0] and self._plain_f32(self.blobs[in_], blob)
-                        and blob.size >= self._CHUNK):
-                    deferred = blob
-                else:
-                    self._assign(self.blobs[in_], blob)          # blob.data[...] = arr, as pycaffe
-        if not fast_path:
+                self._assign(self.blobs[in_], blob)              # blob.data[...] = arr, as pycaffe
+        eng = self._engine
+        eng.cfg.update(_hot_path_cfg())
+        if eng.tail is None or eng.has_python or len(self.inputs) != 2:
             return self._forward_generic(blobs)
         data_blob = self.blobs[self.inputs[0]]
         info = self.blobs[self.inputs[1]]._host.reshape(-1)
@@ -204,25 +197,10 @@ class Net(object):
         info = (float(info[0]), float(info[1]), float(info[2]))
         stream = torch.cuda.current_stream()
         t1 = _now() if prof is not None else 0.0
-        if deferred is not None and not eng.has_graph(data_blob.shape, info):
-            self._assign(data_blob, deferred)                    # first forward of this shape: plain copy, then capture
-            deferred = None
         for attempt in (0, 1):
             eng.guard.zero_()
             # `.data` of an input blob is page-locked: the upload reads it directly (valid until the sync below)
-            if deferred is not None:
-                src, pin = torch.from_numpy(deferred).reshape(-1), data_blob._tview.reshape(-1)
-
-                def feed(x, src=src, pin=pin):
-                    # blob.data[...] = arr and the upload, pipelined: while chunk k crosses PCIe the host copies chunk k + 1
-                    xf = x.reshape(-1)
-                    for o in range(0, src.numel(), self._CHUNK):
-                        pin[o:o + self._CHUNK].copy_(src[o:o + self._CHUNK])
-                        xf[o:o + self._CHUNK].copy_(pin[o:o + self._CHUNK], non_blocking=True)
-                pack = eng.forward_cached(data_blob._tview, info, feed=feed)
-                deferred = None                                  # a guard retry re-uploads from the page-locked blob
-            else:
-                pack = eng.forward_cached(data_blob._tview, info)
+            pack = eng.forward_cached(data_blob._tview, info)
             self._guard_host.copy_(eng.guard, non_blocking=True)
             if pack is not None:
                 if self._out_host is None or self._out_host.numel() < pack.numel():
@@ -325,20 +303,14 @@ class Net(object):
         outs = set(list(tops) + list(blobs or []))
         return {out: self.blobs[out].data for out in outs}
 
-    _CHUNK = 1 << 20                                             # floats per pipelined copy / upload chunk (4 MB)
-
-    @staticmethod
-    def _plain_f32(blob, arr):
-        return (isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.shape == blob.data.shape
-                and arr.flags.c_contiguous and arr.flags.writeable and blob._tview is not None)
-
     @staticmethod
     def _assign(blob, arr):
         """``blob.data[...] = arr`` -- through torch's multi-threaded copy when the array is a plain float32 block of the
         blob's shape (a 24 MB level blob per forward), NumPy's broadcasting assignment otherwise."""
         import torch
         host = blob.data
-        if Net._plain_f32(blob, arr) and arr.size >= (1 << 16):
+        if (isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.shape == host.shape and arr.flags.c_contiguous
+                and arr.size >= (1 << 16) and blob._tview is not None):
             blob._tview.copy_(torch.from_numpy(arr))
         else:
             host[...] = arr
