@@ -61,11 +61,28 @@ def set_device(device_id):
     torch.cuda.set_device(int(device_id))
 
 
+_ref_cfg = [None, False]          # [the reference's cfg object, looked up?]
+
+
 def _hot_path_cfg():
     """TEST.N_DETS_PER_MODULE / SCORE_THRESH / ANCHOR_MIN_SIZE as the ProposalLayer reads them at forward time
-    (``proposal_layer.py:88-92``); defaults of ``configs/default.toml`` when the reference's cfg is not importable."""
+    (``proposal_layer.py:88-92``); defaults of ``configs/default.toml`` when the reference's cfg is not importable.
+    The module lookup happens once (a failing import per forward cost ~0.1 ms); the VALUES are read at every forward,
+    like the reference does."""
+    if not _ref_cfg[1]:
+        _ref_cfg[1] = True
+        try:
+            import sys
+            mod = sys.modules.get("utils.get_config")
+            if mod is None:
+                from utils import get_config as mod    # the reference's own config module, when running inside its tree
+            _ref_cfg[0] = mod.cfg
+        except Exception:
+            _ref_cfg[0] = None
+    cfg = _ref_cfg[0]
+    if cfg is None:
+        return dict(pre_nms_topn=10000, score_thresh=0.002, min_size=0.0)
     try:
-        from utils.get_config import cfg           # the reference's own config object, when running inside its tree
         return dict(pre_nms_topn=int(cfg.TEST.N_DETS_PER_MODULE), score_thresh=float(cfg.TEST.SCORE_THRESH),
                     min_size=float(cfg.TEST.ANCHOR_MIN_SIZE))
     except Exception:
