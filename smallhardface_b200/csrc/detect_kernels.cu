@@ -718,23 +718,26 @@ __global__ void __launch_bounds__(kMaskSweepThreads) mask_sweep_kernel(
     if (tid > b && tid < nb) {
       unsigned long long hb = hbits;
       while (hb) {
-        // up to 8 independent loads in flight, then the (order-dependent) bit logic
-        unsigned long long rows[8];
-        int rr[8], cnt = 0;
+        // up to 32 independent loads in flight (the step is L2-latency bound: one round trip per batch), then the
+        // order-dependent bit logic
+        constexpr int kBatch = 32;
+        unsigned long long rows[kBatch];
+        unsigned long long todo = hb;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (hb) {
-            rr[q] = __ffsll((long long)hb) - 1;
-            hb &= hb - 1;
-            rows[q] = M[(size_t)(b * 64 + rr[q]) * mask_words + tid];
-            cnt = q + 1;
+        for (int q = 0; q < kBatch; ++q) {
+          if (todo) {
+            const int r = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            rows[q] = M[(size_t)(b * 64 + r) * mask_words + tid];
           }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q < cnt) {
+        for (int q = 0; q < kBatch; ++q) {
+          if (hb) {
+            const int r = __ffsll((long long)hb) - 1;
+            hb &= hb - 1;
             const unsigned long long mem = rows[q] & alive;
-            if (VOTE && mem != rows[q]) M[(size_t)(b * 64 + rr[q]) * mask_words + tid] = mem;
+            if (VOTE && mem != rows[q]) M[(size_t)(b * 64 + r) * mask_words + tid] = mem;
             alive &= ~mem;
           }
         }

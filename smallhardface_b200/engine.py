@@ -295,11 +295,11 @@ class GpuNet:
                     raise L.ShfError("conv %s: only stride-1, ungrouped, square kernels are on the hot path" % l.name)
                 cin = w.shape[1]
                 st = dict(relu=relu, k=p["kh"], dil=p["dh"], cout=p["num_output"], cin=cin, top=top,
-                          bias=None if b is None else torch.from_numpy(np.ascontiguousarray(b, F32)).to(dev))
+                          bias=None if b is None else torch.from_numpy(np.array(b, dtype=F32)).to(dev))
                 if cin == 3:
                     if not (p["kh"] == 3 and p["ph"] == 1 and p["dh"] == 1 and p["num_output"] == 64):
                         raise L.ShfError("conv %s: 3-channel convs must be 3x3 pad 1 with 64 outputs" % l.name)
-                    st["w"] = torch.from_numpy(np.ascontiguousarray(w, F32)).to(dev)
+                    st["w"] = torch.from_numpy(np.array(w, dtype=F32)).to(dev)
                     packed1, k1 = pack_conv1_weights(w)
                     st["wtc"] = torch.from_numpy(packed1).to(dev)
                     st["scale"] = float(2.0 ** (-k1))
@@ -352,7 +352,7 @@ class GpuNet:
                 if not (p["group"] == w.shape[0] == p["num_output"] and w.shape[1] == 1 and not p["bias_term"]
                         and p["kh"] == p["kw"] and p["sh"] == p["sw"] and p["ph"] == p["pw"] and p["dh"] == 1):
                     raise L.ShfError("deconv %s: only depthwise, bias-free, square deconvolutions are on the hot path" % l.name)
-                self.ops.append(("deconv", l, dict(w=torch.from_numpy(np.ascontiguousarray(w, F32)).to(dev),
+                self.ops.append(("deconv", l, dict(w=torch.from_numpy(np.array(w, dtype=F32)).to(dev),
                                                    k=p["kh"], s=p["sh"], pad=p["ph"])))
             elif l.type == "Reshape":
                 raise L.ShfError("Reshape %s outside the detection tail is not supported" % l.name)
@@ -432,7 +432,7 @@ class GpuNet:
         fused.add(prop.name)
         dev = self.device
         Cf = heads[0][1].shape[1]
-        t = lambda x: torch.from_numpy(np.ascontiguousarray(x, F32)).to(dev)
+        t = lambda x: torch.from_numpy(np.array(x, dtype=F32)).to(dev)
         shapes = spec.infer_shapes({})
         if len({tuple(shapes[h[0]]) for h in heads}) != 1 or any(h[1].shape[1] != Cf for h in heads):
             raise L.ShfError("detection tail: the head feature maps %s must share one shape" % [h[0] for h in heads])
