@@ -237,6 +237,91 @@ def test_fast_format_guard_falls_back_to_split_fp16(tmp_path, factor, why):
     assert ws < SCORE_TOL and wb < BOX_TOL
 
 
+def test_fast_format_guard_through_the_caffe_net_surface(tmp_path):
+    """The same guard inside `caffe.Net.forward` (CUDA-graph path): the forward that trips it is repeated on split fp16
+    before it returns, so the caller never sees the out-of-window result."""
+    import warnings
+    from oracle import preprocess as PRE
+    from smallhardface_b200 import compat
+    compat.install()
+    import caffe
+    proto, model = _rescaled_deployment(tmp_path, 64.0)
+    onet = IndepNet(proto, model, engine="torch")
+    net = caffe.Net(proto, model, caffe.TEST)
+    im = deploy.synthetic_image(5, (160, 224))
+    s = 1.25
+    blob = PRE.get_image_blobs(im, [s])[0]
+    data = PRE.pad_to_multiple(blob).astype(F32, copy=False)
+    info = np.array([[blob.shape[2], blob.shape[3], s]], F32)
+    net.blobs["data"].reshape(*data.shape)
+    net.blobs["im_info"].reshape(1, 3)
+    with warnings.catch_warnings(record=True) as wrn:
+        warnings.simplefilter("always")
+        out = net.forward(data=data, im_info=info)
+    assert net._engine.fast_disabled and any("exponent window" in str(x.message) for x in wrn)
+    ref = onet.forward(data=data, im_info=info)
+    ws, wb = match_rows(out["boxes"][:, 1:], out["cls_prob"][:, 1], ref["boxes"][:, 1:], ref["cls_prob"][:, 1])
+    assert ws < SCORE_TOL and wb < BOX_TOL
+    out2 = net.forward(data=data, im_info=info)                  # the replayed split-fp16 graph: same answer, no warning
+    assert np.array_equal(out2["boxes"], out["boxes"])
+
+
+def test_plugin_graph_cache_eviction_keeps_results_right(nets):
+    """Many level shapes through one `caffe.Net` with a tiny graph budget: graphs are evicted and re-captured, every
+    forward still equals the eager engine."""
+    from smallhardface_b200 import compat
+    compat.install()
+    import caffe
+    dil, proto, model, gnet, onet = nets
+    net = caffe.Net(proto, model, caffe.TEST)
+    net._engine.graph_max_entries = 2
+    rng = np.random.RandomState(0)
+    shapes = [(32, 48), (48, 32), (64, 64), (32, 48), (80, 48), (48, 32), (64, 64)]
+    first = {}
+    for hw in shapes:
+        x = (rng.rand(1, 3, *hw) * 255 - 110).astype(F32) if hw not in first else first[hw][0]
+        info = np.array([[hw[0] - 3, hw[1] - 5, 1.0]], F32)
+        net.blobs["data"].reshape(*x.shape)
+        net.blobs["im_info"].reshape(1, 3)
+        out = net.forward(data=x, im_info=info)
+        got = (out["boxes"].copy(), out["cls_prob"].copy())
+        if hw in first:
+            assert np.array_equal(got[0], first[hw][1]) and np.array_equal(got[1], first[hw][2]), hw
+        else:
+            first[hw] = (x, got[0], got[1])
+        assert len(net._engine._graphs) <= 2
+    assert len(first) == 4 and all(len(v[1]) >= 1 for v in first.values())
+
+
+@pytest.mark.parametrize("hw", [(33, 47), (17, 200), (16, 16)])
+def test_detector_odd_and_tiny_sizes_vs_oracle(nets, hw):
+    """Image sizes that are not multiples of 16 (every level gets padded), very wide, and the smallest the net accepts."""
+    dil, proto, model, gnet, onet = nets
+    cfg = DetectConfig(scales=(300, 600))
+    det = Detector(proto, model, "cuda:0", cfg)
+    im = deploy.synthetic_image(40 + hw[0], hw)
+    b = det.detect_device(det.upload([im]))
+    got = det.download(b, 1)[0]
+    raw = det.raw_detections(b, 0)
+    probs, boxes = OD.detect_raw(onet, im, scales=cfg.scales, flip=True)
+    ref_raw = OD.threshold_dets(probs, boxes, 0.05)
+    if len(ref_raw):
+        ws, wb = match_rows(raw[:, :4], raw[:, 4], ref_raw[:, :4], ref_raw[:, 4])
+        assert ws < SCORE_TOL and wb < BOX_TOL
+    ref = OP.bbox_vote(raw.copy(), 0.4)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < BOX_TOL
+
+
+def test_detector_image_without_detections_returns_the_reference_placeholder(nets):
+    """`bbox_vote` of an empty detection list returns the single row [10, 10, 20, 20, 1e-4] (lib/test.py:184-186)."""
+    dil, proto, model, gnet, onet = nets
+    det = Detector(proto, model, "cuda:0", DetectConfig(scales=(100, 300), thresh=0.9999))      # nothing clears 0.9999
+    got = det.detect([deploy.synthetic_image(3, (64, 96))])[0]
+    assert got.shape == (1, 5) and np.allclose(got[0], [10, 10, 20, 20, 1e-4])
+    det = Detector(proto, model, "cuda:0", DetectConfig(scales=(100, 300), thresh=0.9999, nms_method="NMS"))
+    assert det.detect([deploy.synthetic_image(3, (64, 96))])[0].shape == (0, 5)
+
+
 def test_fp16_overflow_raises_instead_of_returning_garbage(tmp_path):
     from smallhardface_b200.engine import RangeError
     proto, model = _rescaled_deployment(tmp_path, 400.0)          # activations of several 1e5: beyond fp16 in any format
