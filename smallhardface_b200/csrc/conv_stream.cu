@@ -257,6 +257,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     auto commit = [&](uint32_t bar) { if (CTAS == 2) umma2_commit(bar); else umma_commit(bar); };
     int sa = 0, gp = 0;
     uint32_t pha = 0;
+    const bool grouped = (taps == 9) && (nb >= 4);            // streaming path: three weight stages per single-thread region
+    const uint32_t row_pitch = (uint32_t)(p.dil * p.xw) * 128u;   // bytes from one kernel row of the halo to the next
     if (p.b_resident) {
       // ---- resident weights (conv1_2: one N tile, all taps in the ring): wait for them ONCE, then every halo is one
       //      single-thread region that issues all of its taps back to back -- no per-tap barrier wait, election or
@@ -310,6 +312,38 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             mbar_wait(full_a(sa), pha);
             const uint32_t a_base = smem_base + (uint32_t)sa * a_bytes;
             uint32_t a_off = 0;
+            if (grouped) {
+              // 3x3 kernels, ring of >= 4 weight stages: one single-thread region per KERNEL ROW (three weight stages,
+              // 24 / 36 MMAs) -- the barrier waits, the election and the ring bookkeeping are paid once per three stages;
+              // every stage is still released by its own commit as soon as its MMAs retire
+              for (int row = 0; row < 3; ++row) {
+                int s3[3];
+                uint32_t p3[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  s3[j] = sb; p3[j] = phb;
+                  if (++sb == nb) { sb = 0; phb ^= 1; }
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) mbar_wait(full_b(s3[j]), p3[j]);
+                tc_fence_after();
+                if (issuer) {
+#pragma unroll
+                  for (int j = 0; j < 3; ++j) {
+                    issue_stage(d_main, (((a_base + a_off + (uint32_t)j * tap_dx) & 0x3FFFFu) >> 4) | lbo,
+                                (((b_ring + (uint32_t)s3[j] * b_bytes) & 0x3FFFFu) >> 4) | lbo, j == 0 ? opened : 1u);
+                    commit(empty_b(s3[j]));
+                  }
+                  if (row == 2) {                 // last row of this halo: hand the A stage back as well
+                    commit(empty_a(sa));
+                    if (cc == c_end - 1) commit(acc_full(set));     // ... and, after the phase's last chunk, the accumulators
+                  }
+                }
+                __syncwarp();
+                opened = 1u;
+                a_off += row_pitch;
+              }
+            } else {
             int s = 0;
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(full_b(sb), phb);
@@ -328,6 +362,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               if (++sb == nb) { sb = 0; phb ^= 1; }
               a_off += tap_dx;
               if (++s == ktaps) { s = 0; a_off += tap_dy; }
+            }
             }
             if (++sa == na) { sa = 0; pha ^= 1; }
           }

@@ -66,7 +66,7 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "sm__pipe
         "launch__cluster_size", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
 out = []
 for rep in sorted(os.listdir(go)):
-    if not (rep.startswith(tag) and rep.endswith(".ncu-rep")): continue
+    if not (rep.startswith(tag + "_") and rep.endswith(".ncu-rep")): continue
     r = subprocess.run(["ncu", "-i", os.path.join(go, rep), "--page", "raw", "--csv"], capture_output=True, text=True)
     rows = list(csv.reader(r.stdout.splitlines()))
     if len(rows) < 3: continue
