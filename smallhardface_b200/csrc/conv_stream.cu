@@ -50,6 +50,7 @@ struct StreamParams {
   int chunks_per_phase;       // G
   int ctot, cout_offset, relu;
   int in_fmt, out_fmt;        // SHF_FMT_* of the input (and weight) planes / of the tensors written
+  int group_rows;             // streaming path: one MMA-issue region per kernel row (3 weight stages) instead of per tap
   int b_resident;             // the whole weight tensor fits the B ring (one stage per (chunk, tap)): load it once per CTA
   int probe;                  // SHF_PROBE_EPI timing probes (wrong results): 1 = no global stores, 2 = drain only
   float out_scale;
@@ -257,7 +258,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     auto commit = [&](uint32_t bar) { if (CTAS == 2) umma2_commit(bar); else umma_commit(bar); };
     int sa = 0, gp = 0;
     uint32_t pha = 0;
-    const bool grouped = (taps == 9) && (nb >= 4);            // streaming path: three weight stages per single-thread region
+    const bool grouped = (taps == 9) && (nb >= 4) && p.group_rows;   // streaming path: three weight stages per single-thread region
     const uint32_t row_pitch = (uint32_t)(p.dil * p.xw) * 128u;   // bytes from one kernel row of the halo to the next
     if (p.b_resident) {
       // ---- resident weights (conv1_2: one N tile, all taps in the ring): wait for them ONCE, then every halo is one
@@ -606,6 +607,11 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   p.cout_offset = out_channel_offset;
   p.relu = relu;
   p.in_fmt = in_format;
+  {
+    static int group_rows = -1;               // A/B switch for profiling runs: SHF_CONV_GROUP_ROWS=0 restores per-tap regions
+    if (group_rows < 0) { const char* e = getenv("SHF_CONV_GROUP_ROWS"); group_rows = (e && e[0] == '0') ? 0 : 1; }
+    p.group_rows = group_rows;
+  }
   p.probe = 0;
   if (const char* e = shf_probe_env("SHF_PROBE_EPI")) p.probe = atoi(e);
   p.out_fmt = out_format;
