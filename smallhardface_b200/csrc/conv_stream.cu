@@ -608,8 +608,11 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   p.relu = relu;
   p.in_fmt = in_format;
   {
-    static int group_rows = -1;               // A/B switch for profiling runs: SHF_CONV_GROUP_ROWS=0 restores per-tap regions
-    if (group_rows < 0) { const char* e = getenv("SHF_CONV_GROUP_ROWS"); group_rows = (e && e[0] == '0') ? 0 : 1; }
+    // A/B switch for profiling runs.  Same-box alternating runs (profiles/r02_ab_group_rows.txt) put the per-tap regions
+    // ~1 % ahead of the per-kernel-row grouping (2048 level 691 vs 672 TFLOP/s, bench 106.5 vs 105.3 images/s), so
+    // per-tap is the default and SHF_CONV_GROUP_ROWS=1 selects the grouping.
+    static int group_rows = -1;
+    if (group_rows < 0) { const char* e = getenv("SHF_CONV_GROUP_ROWS"); group_rows = (e && e[0] == '1') ? 1 : 0; }
     p.group_rows = group_rows;
   }
   p.probe = 0;
