@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  // [A tile 16 KB][B1 8 KB][B2 8 KB][staging 4 x 4 KB][mbarrier 8][tmem slot 4][bias 256]
+  // [A tile 16 KB][B1 8 KB][B2 8 KB][staging 4 x 4 KB][mbarrier 8][tmem slot 4][bias 256][halo 540 words]
   uint8_t* a_tile = smem;
   uint8_t* b1 = smem + 16384;
   uint8_t* b2 = smem + 24576;
@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
   const uint32_t bar = smem_base + 49152;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 49152 + 8);
   float* bias_s = reinterpret_cast<float*>(smem + 49152 + 16);
+  uint32_t* halo_s = reinterpret_cast<uint32_t*>(smem + 49152 + 16 + 256);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m = threadIdx.x;                      // operand / accumulator row = pixel (y_local * 8 + x_local)
@@ -79,39 +80,72 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
   uint32_t phase = 0;
   float gmax = 0.f;
 
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-    int q = t;
-    const int x0 = (q % p.tiles_x) * kTW;
-    q /= p.tiles_x;
-    const int y0 = (q % p.tiles_y) * kTH;
-    const int img = q / p.tiles_y;
-    const int y = y0 + (m >> 3), x = x0 + (m & 7);
-    // ---- this pixel's operand row: 27 taps, split to fp16 hi / lo ----
-    {
-      __half hi[32], lo[32];
+  // ---- halo staging (r02b): the 18 x 10 x 3 input patch of a tile is fetched ONCE by the CTA (each thread owns up to
+  //      five fixed patch positions), split to fp16 hi / lo there and parked in shared memory as (hi | lo << 16) words;
+  //      a pixel's operand row is then 27 LDS + 28 byte permutes.  The per-pixel version issued 27 predicated global
+  //      loads, 27 splits and their address arithmetic per thread: 630 of the loop's 1740 instructions in a kernel
+  //      that ncu showed issue-bound (215 M warp instructions for 1 GB of output, 2.9 TB/s).
+  constexpr int kHW = kTW + 2, kHH = kTH + 2, kHaloWords = 3 * kHH * kHW;      // 540
+  constexpr int kPer = (kHaloWords + kC1Threads - 1) / kC1Threads;             // 5
+  int h_rs[kPer];            // (channel << 16) | (row << 8) | column inside the patch, or -1 when the slot is unused
 #pragma unroll
-      for (int k = 27; k < 32; ++k) { hi[k] = __float2half(0.f); lo[k] = __float2half(0.f); }
+  for (int i = 0; i < kPer; ++i) {
+    const int idx = (int)threadIdx.x + i * kC1Threads;
+    const int c = idx / (kHH * kHW), rem = idx % (kHH * kHW), r = rem / kHW, s2 = rem % kHW;
+    h_rs[i] = idx < kHaloWords ? ((c << 16) | (r << 8) | s2) : -1;
+  }
+  float nxt[kPer];           // the next tile's patch values, in flight across the current tile's MMA wait + epilogue
+  int nx0 = 0, ny0 = 0, nimg = 0;                  // ... and its origin (decoded once per tile)
+  auto prefetch = [&](int t) {
+    const unsigned tx = (unsigned)p.tiles_x, ty = (unsigned)p.tiles_y;
+    unsigned q = (unsigned)t;
+    const int x0 = (int)(q % tx) * kTW;
+    q /= tx;
+    const int y0 = (int)(q % ty) * kTH, img = (int)(q / ty);
+    nx0 = x0; ny0 = y0; nimg = img;
+    const float* org = p.in + (size_t)img * 3 * p.H * p.W + ((long long)(y0 - 1) * p.W + (x0 - 1));
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int c = h_rs[i] >> 16, r = (h_rs[i] >> 8) & 255, s2 = h_rs[i] & 255;
+      const int iy = y0 - 1 + r, ix = x0 - 1 + s2;
+      const bool ok = h_rs[i] >= 0 && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+      nxt[i] = ok ? __ldg(org + ((c * p.H + r) * p.W + s2)) : 0.f;      // zero padding = skipped loads
+    }
+  };
+  if ((int)blockIdx.x < p.total_tiles) prefetch(blockIdx.x);
+  const uint32_t* my_halo = halo_s + (m >> 3) * kHW + (m & 7);
+
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    const int x0 = nx0, y0 = ny0, img = nimg;
+    const int y = y0 + (m >> 3), x = x0 + (m & 7);
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      __half hi, lo;
+      split_h2(nxt[i], hi, lo);
+      if (h_rs[i] >= 0)
+        halo_s[threadIdx.x + i * kC1Threads] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
+    __syncthreads();
+    // ---- this pixel's operand row: 27 taps as [hi(k = 0..31) | lo(k = 0..31)], k = c*9 + r*3 + s ----
+    {
+      uint32_t v[32];
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0u;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int iy = y + r - 1;
-          const float* row = p.in + (((size_t)img * 3 + c) * p.H + iy) * p.W;
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int ix = x + s - 1;
-            const float v = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? __ldg(row + ix) : 0.f;
-            split_h2(v, hi[c * 9 + r * 3 + s], lo[c * 9 + r * 3 + s]);
-          }
-        }
+          for (int s2 = 0; s2 < 3; ++s2) v[c * 9 + r * 3 + s2] = my_halo[(c * kHH + r) * kHW + s2];
       uint8_t* arow = a_tile + m * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const __half* src = (j < 4) ? hi + 8 * j : lo + 8 * (j - 4);
         uint32_t w4[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          w4[e] = (uint32_t)__half_as_ushort(src[2 * e]) | ((uint32_t)__half_as_ushort(src[2 * e + 1]) << 16);
+        for (int e = 0; e < 4; ++e) {
+          const int k0 = 8 * (j & 3) + 2 * e;
+          w4[e] = __byte_perm(v[k0], v[k0 + 1], j < 4 ? 0x5410 : 0x7632);     // the hi halves / the lo halves of two taps
+        }
         *reinterpret_cast<uint4*>(arow + ((j ^ (m & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
     }
@@ -125,6 +159,7 @@ __global__ void __launch_bounds__(kC1Threads, 4) conv1_tc_kernel(const C1Params 
       for (int k = 0; k < 2; ++k) umma_f16(tmem_acc, a_desc + 2 * k, b2_desc + 2 * k, idesc, 1u);
       umma_commit(bar);
     }
+    if (t + (int)gridDim.x < p.total_tiles) prefetch(t + (int)gridDim.x);
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -192,7 +227,7 @@ extern "C" int shf_conv1_tc(const float* in_nchw, const void* w_packed, const fl
   p.total_tiles = p.tiles_x * p.tiles_y * batch;
   p.out_scale = out_scale;
   p.guard = range_guard;
-  const int smem_bytes = 1024 + 49152 + 16 + 256;
+  const int smem_bytes = 1024 + 49152 + 16 + 256 + 540 * 4;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   static bool attr[64] = {};                     // function attributes are per device
