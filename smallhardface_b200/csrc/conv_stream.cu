@@ -571,7 +571,17 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   SHF_REQUIRE((long long)W * out_channels_total < (1ll << 29) && (long long)W * pool_channels_total < (1ll << 29),
               "shf_conv_igemm: a row of %d pixels x %d channels overflows the epilogue's 32-bit in-tile offsets", W,
               out_channels_total);
-  const int bn = (cout % 128 == 0) ? 128 : 64;
+  // N tile: 128 output channels, or 64 when the layer has 64-channel granularity -- or when 128-wide tiles would leave
+  // more than half of the CTA pairs idle (the deep layers of the small pyramid levels, batch 1 on the plugin path:
+  // conv4_x of a 304-px level is 9 pixel tile pairs x 4 channel tiles on 74 SM pairs, each walking K = 4608 alone).
+  // Twice the tiles at half the MMA time each; the weight packing does not depend on the tile width.
+  int bn = (cout % 128 == 0) ? 128 : 64;
+  static int small_bn64 = -1;                 // A/B switch: SHF_CONV_SMALL_BN64=0 keeps 128-wide tiles everywhere
+  if (small_bn64 < 0) { const char* e = getenv("SHF_CONV_SMALL_BN64"); small_bn64 = (e && e[0] == '0') ? 0 : 1; }
+  if (bn == 128 && small_bn64) {
+    const long long px_tiles = (long long)(((W + kTW - 1) / kTW + ctas - 1) / ctas) * ((H + kTH - 1) / kTH) * batch;
+    if (px_tiles * (cout / 128) * 2 <= sm_count() / ctas) bn = 64;
+  }
   StreamParams p;
   p.H = H; p.W = W; p.batch = batch;
   p.cin_chunks = cin / 64;
