@@ -428,10 +428,22 @@ def _fmt_float(v: float) -> str:
         else np.format_float_scientific(f32, unique=True, trim="-")
 
 
+_CESC = {"\\": "\\\\", "'": "\\'", '"': '\\"', "\n": "\\n", "\r": "\\r", "\t": "\\t"}
+
+
 def _fmt_scalar(typ: str, v) -> str:
     if typ == "string":
-        s = v.replace("\\", "\\\\").replace('"', '\\"').replace("\n", "\\n")
-        return '"%s"' % s
+        # protobuf's text printer (text_encoding.CEscape): \\ \' \" \n \r \t, other non-printable bytes as 3-digit octal
+        out = []
+        for ch in v:
+            o = ord(ch)
+            if ch in _CESC:
+                out.append(_CESC[ch])
+            elif o < 0x20 or o == 0x7f:
+                out.append("\\%03o" % o)
+            else:
+                out.append(ch)
+        return '"%s"' % "".join(out)
     if typ == "bool":
         return "true" if v else "false"
     if typ.startswith("enum:"):

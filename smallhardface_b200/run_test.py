@@ -1,0 +1,185 @@
+"""``train_test.py --train false`` in Python 3 on the device-resident pipeline: the same command line,
+configuration files, deploy-prototxt rewriting, dataset partition, detection cache and result files as the reference's
+entry point (``train_test.py:33-137``, ``lib/test.py:290-356``), with ``Detector.detect`` in the place of the
+per-pass ``caffe.Net.forward`` loop.
+
+    python -m smallhardface_b200.run_test --root <checkout with configs/ and models/> --conf configs/smallhardface.toml \\
+        --amend DATA_DIR <images> TEST.DB general_png TEST.MODEL <caffemodel> TEST.GPU_ID "[0]"
+
+Under ``torchrun`` every rank takes the reference's contiguous shard (``lib/test.py:329-335``) and the boxes are
+exchanged with the path's one all-gather (``parallel.py``); rank 0 writes the files.  The unmodified reference driver
+on the drop-in ``caffe`` module is ``tools/run_reference_driver.py``; this module is the variant that keeps images and
+detections on the GPU between the layers the reference round-trips through NumPy.
+
+Datasets: the ``general_<ext>`` loader (``lib/datasets/general.py:19-79``: every ``*.<ext>`` under ``DATA_DIR``, results as
+text files under the output directory).  The WIDER / FDDB / AFW / PASCAL loaders need their annotation files and are out
+of scope (SURVEY section 2 OUT); their result format is the same writer (``writers.write_detections``).
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import logging
+import os
+import os.path as osp
+import pickle
+import sys
+from typing import List
+
+import numpy as np
+
+from . import config as C
+from . import prototxt
+from .writers import write_detections
+
+logger = logging.getLogger(__name__)
+
+
+class GeneralImdb:
+    """``lib/datasets/general.py:19-42``: name ``general_<ext>``, images = every file ending in ``.<ext>`` below ``DATA_DIR``
+    in ``os.walk`` order."""
+
+    def __init__(self, data_dir: str, split: str):
+        self.name = "general_" + split
+        self.extension = split
+        self.classes = ["bg", "face"]
+        self.image_paths: List[str] = []
+        for root, _dirs, files in os.walk(data_dir):
+            for f in files:
+                if f.endswith(".{}".format(split)):
+                    self.image_paths.append(osp.join(root, f))
+
+    num_classes = 2
+
+    def __len__(self):
+        return len(self.image_paths)
+
+    def image_path_at(self, i):
+        p = self.image_paths[i]
+        assert osp.exists(p), "Path does not exist: {}".format(p)
+        return p
+
+    def evaluate_detections(self, all_boxes, output_dir="./output/"):
+        """``general.py:44-79``: no ground truth -- write the text files."""
+        write_detections(self.image_paths, all_boxes[1], output_dir, extension=self.extension, strip_leading_slash=True)
+        return "Detection results wrote to {}".format(output_dir)
+
+
+def get_imdb(cfg, name: str):
+    """``lib/datasets/factory.py:9-34`` for the datasets in scope."""
+    if name.startswith("general_") and name[len("general_"):] in ("png", "jpg"):
+        return GeneralImdb(cfg.DATA_DIR, name[len("general_"):])
+    if name.split("_")[0] in ("wider", "fddb", "pascalface", "afw"):
+        raise NotImplementedError("dataset %s needs its annotation files; only general_{png,jpg} is in scope here" % name)
+    raise KeyError("Unknown dataset: {}".format(name))
+
+
+def inference(cfg, imdb, prototxt_path: str, start: int, end: int, thresh: float = 0.05, batch: int = 8, device="cuda:0"):
+    """``lib/test.py:220-267`` inference_worker for images [start, end): returns ``all_boxes[class][image]``."""
+    import cv2
+    from .detector import Detector
+    det = Detector(prototxt_path, cfg.TEST.MODEL, device, C.detect_config(cfg, thresh=thresh))
+    all_boxes = [[[] for _ in range(end - start)] for _ in range(imdb.num_classes)]
+    for i0 in range(start, end, batch):
+        paths = [imdb.image_path_at(i) for i in range(i0, min(i0 + batch, end))]
+        images = [cv2.imread(p) for p in paths]
+        for p, im in zip(paths, images):
+            if im is None:
+                raise IOError("cv2.imread failed on {}".format(p))
+        for j, d in enumerate(det.detect(images)):
+            all_boxes[1][i0 - start + j] = d
+        logger.info("im_detect: %d/%d", min(i0 + batch, end) - start, end - start)
+    return all_boxes
+
+
+def test_net(cfg, imdb, output_dir: str, target_test: str, thresh: float = 0.05, no_cache: bool = False, batch: int = 8):
+    """``lib/test.py:290-356``.  The detection cache is the reference's ``detections.pkl``."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    det_file = osp.join(output_dir, "detections.pkl")
+    dets = None
+    if not no_cache and osp.exists(det_file):
+        try:
+            with open(det_file, "rb") as f:
+                dets = pickle.load(f)
+            logger.info("Loading detections from cache: %s", det_file)
+        except Exception:
+            logger.warning("Could not load the cached detections file, detecting from scratch!")
+    if dets is None:
+        from .parallel import shard_range
+        a, b = shard_range(len(imdb), world, rank)
+        dev = "cuda:%d" % (int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else _first_gpu(cfg))
+        mine = inference(cfg, imdb, target_test, a, b, thresh, batch, dev)
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine[1])          # variable-length float64 rows: the object gather of the CLI
+            dets = [[[] for _ in range(len(imdb))], [d for part in parts for d in part]]
+        else:
+            dets = mine
+        assert len(dets[1]) == len(imdb), "Detection result compromised"
+        if not no_cache and rank == 0:
+            with open(det_file, "wb") as f:
+                pickle.dump(dets, f, pickle.HIGHEST_PROTOCOL)
+    result = imdb.evaluate_detections(dets, output_dir) if rank == 0 else None
+    if rank == 0:
+        logger.info(result)
+    del torch
+    return dets, result
+
+
+def _first_gpu(cfg) -> int:
+    g = cfg.TEST.GPU_ID
+    return int(g[0] if isinstance(g, (list, tuple)) else g)
+
+
+def build_cfg(root: str, conf_file: str = "", set_cfgs=None):
+    """``train_test.py:52-66``."""
+    cfg = C.load_default(root)
+    if conf_file:
+        cfg_path = conf_file if osp.isabs(conf_file) else osp.join(root, conf_file)
+        C.cfg_from_file(cfg, cfg_path)
+    cfg.TEST.NO_CACHE = True
+    if set_cfgs:
+        C.cfg_from_list(cfg, set_cfgs)
+    cfg.LOG.CMD = " ".join(sys.argv)
+    cfg.LOG.TIME = datetime.datetime.now().strftime("%Y_%m_%d_%H_%M_%S")
+    np.random.seed(int(cfg.RNG_SEED))
+    return cfg
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser("Test", description="Give settings")
+    ap.add_argument("--root", default=".", help="checkout holding configs/ and models/ (the reference's working directory)")
+    ap.add_argument("--conf", dest="conf_file", default="")
+    ap.add_argument("--output", default=None, help="base of the output tree (default: <root>/output)")
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--train", default="false")
+    ap.add_argument("--test", default="true")
+    ap.add_argument("--amend", dest="set_cfgs", default=None, nargs=argparse.REMAINDER)
+    args = ap.parse_args(argv)
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)-8s [%(filename)s:%(lineno)d] %(message)s")
+    if args.train.lower() == "true":
+        raise SystemExit("training is outside this framework's scope (SURVEY section 2): pass --train false")
+    cfg = build_cfg(osp.abspath(args.root), args.conf_file, args.set_cfgs)
+    if os.environ.get("WORLD_SIZE", "1") != "1":
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    if cfg.TEST.DEMO.ENABLE:
+        raise NotImplementedError("TEST.DEMO draws boxes with cv2 on one image; use Detector.detect directly")
+    imdb = get_imdb(cfg, cfg.TEST.DB)
+    out_base = args.output or "output"
+    output_dir = C.get_output_dir(cfg, imdb.name, cfg.NAME + "_" + cfg.LOG.TIME, output_dir=out_base)
+    target_test = osp.join(output_dir, "test.prototxt")
+    prototxt.manipulate_test(cfg, cfg.TEST.PROTOTXT, target_test)
+    with open(osp.join(output_dir, "cfgs.txt"), "w") as f:
+        C.cfg_dump({k: cfg[k] for k in cfg if k != "TRAIN"}, f)
+    dets, result = test_net(cfg, imdb, output_dir, target_test, no_cache=cfg.TEST.NO_CACHE, batch=args.batch)
+    return output_dir, dets, result
+
+
+if __name__ == "__main__":
+    main()
