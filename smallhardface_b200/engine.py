@@ -376,6 +376,12 @@ class GpuNet:
             for t in l.tops:
                 if t not in l.bottoms:
                     by_top[t] = l
+        if spec.phase == 0:
+            # proposal_layer.py:83-86 reads cfg.TRAIN.NMS_THRESH, a key configs/default.toml does not define (AttributeError
+            # in the reference), and :182-185 then uses an undefined score_thresh: the TRAIN-phase branch is dead code
+            # there -- no shipped train prototxt contains a ProposalLayer -- so there is no behaviour to reproduce
+            raise L.ShfError("ProposalLayer in a TRAIN-phase net: the reference's TRAIN branch cannot run "
+                             "(cfg.TRAIN.NMS_THRESH does not exist); only the TEST phase is on this path")
         lp = parse_python_param_str(prop.p["param_str"])
         from .anchors import generate_anchors
         anchors = generate_anchors(base_size=lp.get("base_size", 16), ratios=lp.get("ratios", (0.5, 1, 2)),
