@@ -58,6 +58,33 @@ int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const float* bias, 
                         int out_channel_offset, int pool_channels_total, int pool_channel_offset, float out_scale,
                         int relu, int in_format, int out_format, unsigned int* range_guard, void* stream);
 
+/* shf_conv_igemm for a 1x1 kernel with spatial stride (pad 0): the projection shortcuts and downsampling 1x1 convolutions
+ * of a ResNet bottleneck (conv_layer.cpp:8-28 output size (H - 1) / stride + 1).  H x W are the INPUT dims.  The same
+ * tcgen05 kernel reads the activations through a strided TMA view (every stride-th pixel), no gather kernel. */
+int shf_conv_igemm_strided(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
+                           int stride, int cin, int cout, int out_channels_total, int out_channel_offset, float out_scale,
+                           int relu, int in_format, int out_format, unsigned int* range_guard, void* stream);
+
+/* ---- layers a ResNet-style backbone adds (BASELINE north_star names "the ResNet/VGG backbone"; csrc/resnet_kernels.cu) -- */
+/* EltwiseLayer SUM (eltwise_layer.cpp:37-77): out = sum_t coeffs[t] * ins[t] over n_in (<= 4) activation tensors of
+ * `pixels` x C [dev; ins is a HOST array of device pointers], coeffs [host, may be NULL = all 1], optionally followed by the
+ * in-place ReLU of a residual block; written at a channel offset like shf_conv_igemm. */
+int shf_eltwise_sum(const void* const* ins, const float* coeffs, int n_in, void* out, long long pixels, int C,
+                    int out_channels_total, int out_channel_offset, int relu, int in_format, int out_format,
+                    unsigned int* range_guard, void* stream);
+
+/* PoolingLayer MAX with any kernel / stride / pad (pooling_layer.cpp:79-123,140-187: ceil-mode output size, windows clipped
+ * to the image).  shf_pool_out_size is the layer's output-size rule for one dimension (any_pad = pad_h || pad_w). */
+int shf_pool_out_size(int size, int k, int stride, int pad, int any_pad);
+int shf_maxpool(const void* in_h2, void* out_h2, int batch, int H, int W, int C, int kh, int kw, int sh, int sw, int ph, int pw,
+                int format, void* stream);
+
+/* First convolution of a net whose input has 3 channels, square kernel <= 11, stride <= 4 (ResNet conv1: 7x7 stride 2 pad 3):
+ * fp32 NCHW (N,3,H,W) [dev] -> activation tensor (N,HO,WO,64); weights OIHW fp32 [dev] (64,3,k,k) (BatchNorm / Scale already
+ * folded in by the caller), fp32 FMAs.  The VGG16 conv1_1 (3x3 stride 1) stays on shf_conv1_tc. */
+int shf_conv_first(const float* in_nchw, const float* w_oihw, const float* bias, void* out_act, int batch, int H, int W,
+                   int cout, int ksize, int stride, int pad, int relu, int out_format, unsigned int* range_guard, void* stream);
+
 /* Test hook: 8 = the conv kernel on CTA pairs (tcgen05 cta_group::2, the product path and the default), 7 = the same
  * persistent streaming-drain kernel with one CTA per tile (regression twin of the pair protocol; same results). */
 int shf_set_conv_impl(int impl);

@@ -335,6 +335,11 @@ class IndepNet:
                     y = L.max_pool_2x2_fast(xs[0])
                 else:
                     y = L.max_pool(xs[0], (k, k), (s, s), (p, p))
+            elif t == "Eltwise":
+                q = _one(l, "eltwise_param", [])
+                if _one(q, "operation", "SUM") != "SUM":
+                    raise ValueError("only Eltwise SUM is on the hot path")
+                y = L.eltwise_sum(xs, [float(v) for v in _all(q, "coeff")])
             elif t == "Concat":
                 q = _one(l, "concat_param", [])
                 y = np.concatenate(xs, axis=int(_one(q, "axis", _one(q, "concat_dim", 1))))

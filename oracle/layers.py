@@ -270,3 +270,13 @@ def bilinear_filler(shape):
         y = (i // k) % k
         flat[i] = (1 - abs(x / f - c)) * (1 - abs(y / f - c))
     return out
+
+
+def eltwise_sum(xs, coeffs=None):
+    """EltwiseLayer SUM, ``eltwise_layer.cpp:52-57``: ``top = coeff0 * bottom0`` (``caffe_set`` + ``caffe_axpy`` in the
+    reference, i.e. fp32 multiply-adds in bottom order)."""
+    coeffs = [1.0] * len(xs) if not coeffs else list(coeffs)
+    y = np.zeros_like(xs[0], dtype=F32)
+    for c, x in zip(coeffs, xs):
+        y = (y + F32(c) * x.astype(F32)).astype(F32)
+    return y

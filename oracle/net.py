@@ -83,6 +83,10 @@ class OracleNet:
                     y = L.max_pool_2x2_fast(xs[0])
                 else:
                     y = L.max_pool(xs[0], (p["kh"], p["kw"]), (p["sh"], p["sw"]), (p["ph"], p["pw"]))
+            elif t == "Eltwise":
+                if p["operation"] != 1:
+                    raise ValueError("only Eltwise SUM is on the hot path")
+                y = L.eltwise_sum(xs, p["coeff"])
             elif t == "Concat":
                 y = L.concat(xs, p["axis"])
             elif t == "Reshape":

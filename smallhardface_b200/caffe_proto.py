@@ -35,6 +35,7 @@ ENUMS: Dict[str, Dict[str, int]] = {
     "Engine": {"DEFAULT": 0, "CAFFE": 1, "CUDNN": 2},                    # caffe.proto:600-604
     "PoolMethod": {"MAX": 0, "AVE": 1, "STOCHASTIC": 2},                 # caffe.proto:919-923
     "VarianceNorm": {"FAN_IN": 0, "FAN_OUT": 1, "AVERAGE": 2},           # caffe.proto:56-60
+    "EltwiseOp": {"PROD": 0, "SUM": 1, "MAX": 2},                        # caffe.proto:702-706
     "SolverMode": {"CPU": 0, "GPU": 1},
     "SnapshotFormat": {"HDF5": 0, "BINARYPROTO": 1},
 }
@@ -79,6 +80,7 @@ SCHEMA: Dict[str, Dict[str, Tuple[int, str, str]]] = {
         "propagate_down": (11, "bool", "r"),
         "concat_param": (104, "ConcatParameter", "o"),
         "convolution_param": (106, "ConvolutionParameter", "o"),
+        "eltwise_param": (110, "EltwiseParameter", "o"),
         "pooling_param": (121, "PoolingParameter", "o"),
         "relu_param": (123, "ReLUParameter", "o"),
         "softmax_param": (125, "SoftmaxParameter", "o"),
@@ -96,6 +98,9 @@ SCHEMA: Dict[str, Dict[str, Tuple[int, str, str]]] = {
         "bias_term": (4, "bool", "o"), "bias_filler": (5, "FillerParameter", "o"),
     },
     "ConcatParameter": {"concat_dim": (1, "uint32", "o"), "axis": (2, "int32", "o")},  # :496-505
+    "EltwiseParameter": {                                                # caffe.proto:701-713
+        "operation": (1, "enum:EltwiseOp", "o"), "coeff": (2, "float", "r"), "stable_prod_grad": (3, "bool", "o"),
+    },
     "ConvolutionParameter": {                                            # caffe.proto:573-624
         "num_output": (1, "uint32", "o"), "bias_term": (2, "bool", "o"),
         "pad": (3, "uint32", "r"), "kernel_size": (4, "uint32", "r"),
@@ -152,6 +157,7 @@ DEFAULTS: Dict[Tuple[str, str], Any] = {
     ("PoolingParameter", "stride"): 1, ("PoolingParameter", "global_pooling"): False,
     ("PoolingParameter", "engine"): 0,
     ("ConcatParameter", "axis"): 1, ("ConcatParameter", "concat_dim"): 1,
+    ("EltwiseParameter", "operation"): 1, ("EltwiseParameter", "stable_prod_grad"): True,
     ("SoftmaxParameter", "axis"): 1, ("SoftmaxParameter", "engine"): 0,
     ("ReLUParameter", "negative_slope"): 0.0, ("ReLUParameter", "engine"): 0,
     ("ReshapeParameter", "axis"): 0, ("ReshapeParameter", "num_axes"): -1,

@@ -11,21 +11,31 @@ _SCALAR = {"int32": _T.TYPE_INT32, "int64": _T.TYPE_INT64, "uint32": _T.TYPE_UIN
            "bool": _T.TYPE_BOOL, "float": _T.TYPE_FLOAT, "double": _T.TYPE_DOUBLE, "string": _T.TYPE_STRING}
 
 
+_TOP_LEVEL_ENUMS = ("Phase",)
+
+
 def _build():
     fd = descriptor_pb2.FileDescriptorProto(name="shf_caffe.proto", package="caffe", syntax="proto2")
-    for ename, values in ENUMS.items():
+    # `Phase` is a file-level enum in caffe.proto; every other enum is nested in the message that uses it (Engine is
+    # declared once per layer parameter, PoolMethod.MAX and EltwiseOp.MAX would collide at file level)
+    for ename in _TOP_LEVEL_ENUMS:
         e = fd.enum_type.add(name=ename)
-        for k, v in values.items():
+        for k, v in ENUMS[ename].items():
             e.value.add(name=k, number=v)
     for mname, fields in SCHEMA.items():
         m = fd.message_type.add(name=mname)
+        for ename in sorted({typ[5:] for _, typ, _ in fields.values() if typ.startswith("enum:")} - set(_TOP_LEVEL_ENUMS)):
+            e = m.enum_type.add(name=ename)
+            for k, v in ENUMS[ename].items():
+                e.value.add(name=k, number=v)
         for fname, (num, typ, lab) in sorted(fields.items(), key=lambda kv: kv[1][0]):
             f = m.field.add(name=fname, number=num,
                             label=_T.LABEL_OPTIONAL if lab == "o" else _T.LABEL_REPEATED)
             if typ in SCHEMA:
                 f.type, f.type_name = _T.TYPE_MESSAGE, ".caffe." + typ
             elif typ.startswith("enum:"):
-                f.type, f.type_name = _T.TYPE_ENUM, ".caffe." + typ[5:]
+                nested = typ[5:] not in _TOP_LEVEL_ENUMS
+                f.type, f.type_name = _T.TYPE_ENUM, ".caffe." + (mname + "." if nested else "") + typ[5:]
             else:
                 f.type = _SCALAR[typ]
             if lab == "p":

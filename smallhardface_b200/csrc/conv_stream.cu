@@ -547,8 +547,13 @@ int sm_count() {
 static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
-                         int ctas, int in_format, int out_format, unsigned int* range_guard, void* stream) {
+                         int ctas, int in_format, int out_format, unsigned int* range_guard, void* stream,
+                         int in_stride = 1, int in_H = 0, int in_W = 0) {
+  // in_stride > 1 (1x1 kernels only): H x W are the OUTPUT dims, the activations are read through a strided TMA view
+  // of the in_H x in_W input (every in_stride-th pixel) -- conv_layer.cpp:8-28 with kernel 1, pad 0
   SHF_REQUIRE(ctas == 1 || ctas == 2, "shf_conv_igemm: %d CTAs per tile group", ctas);
+  SHF_REQUIRE(in_stride >= 1 && (in_stride == 1 || (ksize == 1 && pool_out_h2 == nullptr)),
+              "shf_conv_igemm: stride %d needs a 1x1 kernel without fused pooling", in_stride);
   SHF_REQUIRE((in_format == SHF_FMT_H2 || in_format == SHF_FMT_HF8) && (out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8),
               "shf_conv_igemm: unknown activation format %d / %d", in_format, out_format);
   if (out_format == SHF_FMT_HF8)
@@ -606,7 +611,8 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   p.b_resident = (cout == bn && p.taps * p.cin_chunks <= p.nb && p.na >= 2 && !shf_probe_env("SHF_PROBE_NO_RESIDENT")) ? 1 : 0;
   if (p.b_resident) p.nb = p.taps * p.cin_chunks;
   if (const char* e = shf_probe_env("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
-  SHF_REQUIRE(p.nb >= 2, "shf_conv_igemm: halo tile of %d bytes leaves no room for the weight ring", p.a_bytes);
+  // (a resident weight tensor may be a single stage: the 64 -> 64 1x1 convolutions of a ResNet bottleneck)
+  SHF_REQUIRE(p.nb >= 2 || p.b_resident, "shf_conv_igemm: halo tile of %d bytes leaves no room for the weight ring", p.a_bytes);
   p.tiles_x = ((W + kTW - 1) / kTW + ctas - 1) / ctas;          // tile pairs along x when ctas == 2
   p.tiles_y = (H + kTH - 1) / kTH;
   p.n_tiles = cout / bn;
@@ -643,7 +649,13 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   {
     uint64_t d[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)batch, 2};
     uint32_t b[5] = {64, (uint32_t)p.xw, (uint32_t)p.xh, 1, 2};
-    if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "activations")) return e;
+    if (in_stride == 1) {
+      if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "activations")) return e;
+    } else {
+      const uint64_t px = (uint64_t)cin * 2, row = px * (uint64_t)in_W, img = row * (uint64_t)in_H;
+      const uint64_t bs[4] = {px * (uint64_t)in_stride, row * (uint64_t)in_stride, img, img * (uint64_t)batch};
+      if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "strided activations", bs)) return e;
+    }
   }
   {
     uint64_t d[4] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)p.taps, 2};
@@ -697,4 +709,17 @@ extern "C" int shf_conv_igemm_pool(const void* in_h2, const void* w_h2, const fl
   return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                               out_channel_offset, out_scale, relu, pool_out_h2, pool_channels_total,
                               pool_channel_offset, g_conv_ctas, in_format, out_format, range_guard, stream);
+}
+
+// 1x1 convolution with stride s (pad 0): the projection shortcuts / downsampling 1x1 convs of a ResNet bottleneck.  H x W
+// are the INPUT dims; the output is ((H - 1) / s + 1) x ((W - 1) / s + 1).  Same kernel, strided TMA view of the input.
+extern "C" int shf_conv_igemm_strided(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch,
+                                      int H, int W, int stride, int cin, int cout, int out_channels_total,
+                                      int out_channel_offset, float out_scale, int relu, int in_format, int out_format,
+                                      unsigned int* range_guard, void* stream) {
+  SHF_REQUIRE(stride >= 1 && stride <= 8 && H >= 1 && W >= 1, "shf_conv_igemm_strided: stride %d on %dx%d", stride, H, W);
+  const int HO = (H - 1) / stride + 1, WO = (W - 1) / stride + 1;
+  return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, HO, WO, cin, cout, 1, 1, out_channels_total,
+                              out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_ctas, in_format, out_format,
+                              range_guard, stream, stride, H, W);
 }

@@ -18,9 +18,10 @@ inline ShfEncodeTiledFn shf_get_encode_fn() {
   return fn;
 }
 
-// fp16 tensor, dims innermost-first, dense strides, 128-byte swizzle, out-of-bounds reads return zero
+// fp16 tensor, dims innermost-first, 128-byte swizzle, out-of-bounds reads return zero.  byte_strides (rank - 1 entries:
+// the byte pitch of dims 1 .. rank-1) = nullptr means dense; a strided view (every s-th pixel of a map) passes its own.
 inline int shf_encode_f16_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box,
-                              const char* what) {
+                              const char* what, const uint64_t* byte_strides = nullptr) {
   ShfEncodeTiledFn fn = shf_get_encode_fn();
   SHF_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gdim[5], gstride[4];
@@ -31,7 +32,7 @@ inline int shf_encode_f16_map(CUtensorMap* map, void* base, int rank, const uint
     bdim[i] = box[i];
     estride[i] = 1;
     stride *= dims[i];
-    if (i < rank - 1) gstride[i] = stride;
+    if (i < rank - 1) gstride[i] = byte_strides ? byte_strides[i] : stride;
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, gdim, gstride, bdim, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

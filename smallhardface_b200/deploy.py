@@ -64,6 +64,22 @@ def synthetic_params(spec: NetSpec, seed: int = RNG_SEED) -> Dict[str, np.ndarra
     rng = np.random.RandomState(seed)
     out: Dict[str, np.ndarray] = {}
     for l in spec.layers:
+        if l.type == "BatchNorm":                    # running mean / variance / moving-average factor (batch_norm_layer.cpp:23-45)
+            c = spec.param_shapes[l.param_keys[0]][0]
+            factor = np.float32(0.999 * 50)           # the blobs hold sums scaled by this factor
+            out[l.param_keys[0]] = (rng.standard_normal(c) * 0.1).astype(np.float32) * factor
+            out[l.param_keys[1]] = (0.5 + rng.rand(c)).astype(np.float32) * factor
+            out[l.param_keys[2]] = np.array([factor], dtype=np.float32)
+            continue
+        if l.type == "Scale":
+            c = spec.param_shapes[l.param_keys[0]][0]
+            # the last Scale of a residual branch is damped (as zero-gamma initialisation does) so that activations neither
+            # grow nor vanish through a stack of residual adds
+            gain = 0.5 if l.name.endswith("_branch2c") else 1.0
+            out[l.param_keys[0]] = (gain * (0.8 + 0.4 * rng.rand(c))).astype(np.float32)
+            if len(l.param_keys) > 1:
+                out[l.param_keys[1]] = (rng.standard_normal(c) * 0.05).astype(np.float32)
+            continue
         if l.type not in ("Convolution", "Deconvolution"):
             continue
         for i, key in enumerate(l.param_keys):
@@ -128,5 +144,26 @@ def write_synthetic_deployment(out_dir: str, dilation: bool = True, seed: int = 
         spec = NetSpec(net, TEST)
         params = synthetic_params(spec, seed)
         cp.write_net_binary(model + tmp, params_to_netparameter(spec, params))
+        os.replace(model + tmp, model)
+    return proto, model
+
+
+def write_synthetic_resnet_deployment(out_dir: str, blocks=(3, 4), seed: int = RNG_SEED, input_hw=(224, 224)):
+    """``models.build_resnet_test_net`` + synthetic weights (He-normal convs, plausible BatchNorm statistics, Scale gains)
+    as ``test_resnet.prototxt`` / ``.caffemodel``; returns the two paths."""
+    from .models import build_resnet_test_net
+    os.makedirs(out_dir, exist_ok=True)
+    tag = "resnet_" + "_".join(str(b) for b in blocks)
+    proto = os.path.join(out_dir, "test_%s.prototxt" % tag)
+    model = os.path.join(out_dir, "synthetic_%s_seed%d.caffemodel" % (tag, seed))
+    net = build_resnet_test_net(blocks, input_hw)
+    tmp = ".tmp%d" % os.getpid()
+    if not os.path.exists(proto):
+        with open(proto + tmp, "w") as f:
+            f.write(cp.format_text(net))
+        os.replace(proto + tmp, proto)
+    if not os.path.exists(model):
+        spec = NetSpec(net, TEST)
+        cp.write_net_binary(model + tmp, params_to_netparameter(spec, synthetic_params(spec, seed)))
         os.replace(model + tmp, model)
     return proto, model

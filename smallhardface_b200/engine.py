@@ -291,20 +291,28 @@ class GpuNet:
                 if j < len(layers) and layers[j].type == "ReLU" and layers[j].bottoms == [top] \
                         and layers[j].tops == [top] and layers[j].p["negative_slope"] == 0.0:
                     relu = True
-                if (p["sh"], p["sw"]) != (1, 1) or p["group"] != 1 or p["kh"] != p["kw"] or p["dh"] != p["dw"] or p["ph"] != p["pw"]:
-                    raise L.ShfError("conv %s: only stride-1, ungrouped, square kernels are on the hot path" % l.name)
+                if p["sh"] != p["sw"] or p["group"] != 1 or p["kh"] != p["kw"] or p["dh"] != p["dw"] or p["ph"] != p["pw"]:
+                    raise L.ShfError("conv %s: only ungrouped, square kernels with equal strides are on the hot path" % l.name)
                 cin = w.shape[1]
-                st = dict(relu=relu, k=p["kh"], dil=p["dh"], cout=p["num_output"], cin=cin, top=top,
+                st = dict(relu=relu, k=p["kh"], dil=p["dh"], cout=p["num_output"], cin=cin, top=top, stride=p["sh"],
                           bias=None if b is None else torch.from_numpy(np.array(b, dtype=F32)).to(dev))
-                if cin == 3:
-                    if not (p["kh"] == 3 and p["ph"] == 1 and p["dh"] == 1 and p["num_output"] == 64):
-                        raise L.ShfError("conv %s: 3-channel convs must be 3x3 pad 1 with 64 outputs" % l.name)
+                if cin == 3 and (p["kh"], p["ph"], p["dh"], p["sh"], p["num_output"]) == (3, 1, 1, 1, 64):
                     st["w"] = torch.from_numpy(np.array(w, dtype=F32)).to(dev)
                     packed1, k1 = pack_conv1_weights(w)
                     st["wtc"] = torch.from_numpy(packed1).to(dev)
                     st["scale"] = float(2.0 ** (-k1))
                     self.ops.append(("conv1", l, st))
+                elif cin == 3:
+                    # the first convolution of a ResNet-style backbone (7x7 stride 2 pad 3): fp32 SIMT kernel
+                    if not (p["num_output"] == 64 and p["dh"] == 1 and p["kh"] <= 11 and p["sh"] <= 4 and p["ph"] < p["kh"]):
+                        raise L.ShfError("conv %s: 3-channel convs need 64 outputs, kernel <= 11, stride <= 4, no dilation" % l.name)
+                    st["w"] = torch.from_numpy(np.array(w, dtype=F32)).to(dev)
+                    st["pad"] = p["ph"]
+                    self.ops.append(("conv_first", l, st))
                 else:
+                    if p["sh"] != 1 and not (p["kh"] == 1 and p["ph"] == 0):
+                        raise L.ShfError("conv %s: a spatial stride is supported on 1x1 convolutions only (the ResNet "
+                                         "projection / downsampling form)" % l.name)
                     if p["kh"] not in (1, 3) or (p["kh"] == 3 and p["ph"] != p["dh"]) or (p["kh"] == 1 and p["ph"] != 0):
                         raise L.ShfError("conv %s: need 3x3 with pad == dilation or 1x1 with pad 0" % l.name)
                     if cin % 64 or p["num_output"] % 64:
@@ -318,7 +326,7 @@ class GpuNet:
                         st["w8"] = torch.from_numpy(packed8).to(dev)
                     nxt = j + (1 if relu else 0)
                     pl = layers[nxt] if nxt < len(layers) else None
-                    if (self.fuse_pool and pl is not None and pl.type == "Pooling" and pl.bottoms == [top]
+                    if (self.fuse_pool and p["sh"] == 1 and pl is not None and pl.type == "Pooling" and pl.bottoms == [top]
                             and (pl.p["pool"], pl.p["kh"], pl.p["kw"], pl.p["sh"], pl.p["sw"], pl.p["ph"], pl.p["pw"]) == (0, 2, 2, 2, 2, 0, 0)):
                         st["pool_top"] = pl.tops[0]
                         st["write_full"] = len(consumers.get(top, [])) > 1      # e.g. conv4_3 also feeds conv4_256
@@ -341,11 +349,23 @@ class GpuNet:
                 raise L.ShfError("%s %s does not follow a convolution it can be folded into (unsupported pattern)" % (l.type, l.name))
             if l.type == "ReLU":
                 raise L.ShfError("ReLU %s is not fused into a preceding convolution (unsupported pattern)" % l.name)
+            if l.type == "Eltwise":
+                # the residual add of a ResNet block (eltwise_layer.cpp:37-77) + the in-place ReLU that follows it
+                if l.p["operation"] != 1:
+                    raise L.ShfError("Eltwise %s: only SUM has a CUDA implementation on this path" % l.name)
+                if not 1 <= len(l.bottoms) <= 4:
+                    raise L.ShfError("Eltwise %s: 1..4 bottoms supported" % l.name)
+                top = l.tops[0]
+                relu = (i + 1 < len(layers) and layers[i + 1].type == "ReLU" and layers[i + 1].bottoms == [top]
+                        and layers[i + 1].tops == [top] and layers[i + 1].p["negative_slope"] == 0.0)
+                self.ops.append(("eltwise", l, dict(relu=relu, coeff=[float(c) for c in l.p["coeff"]], top=top)))
+                i += 2 if relu else 1
+                continue
             if l.type == "Pooling":
                 p = l.p
-                if (p["pool"], p["kh"], p["kw"], p["sh"], p["sw"], p["ph"], p["pw"]) != (0, 2, 2, 2, 2, 0, 0):
-                    raise L.ShfError("pool %s: only MAX 2x2 stride 2 is on the hot path" % l.name)
-                self.ops.append(("pool", l, {}))
+                if p["pool"] != 0:
+                    raise L.ShfError("pool %s: only MAX pooling is on the hot path" % l.name)
+                self.ops.append(("pool", l, dict(p)))
             elif l.type == "Deconvolution":
                 p = l.p
                 w = params[l.param_keys[0]]
@@ -360,10 +380,11 @@ class GpuNet:
                 raise L.ShfError("layer %s of type %s has no CUDA implementation on this path" % (l.name, l.type))
             i += 1
         # one range-guard slot per launch that writes an activation tensor; row 0 = written as h2, row 1 = as hf8
-        self.guard_ops = [(k, l.name) for k, l, st in self.ops if k in ("conv1", "conv", "deconv")]
+        writers = ("conv1", "conv", "deconv", "conv_first", "eltwise")
+        self.guard_ops = [(k, l.name) for k, l, st in self.ops if k in writers]
         n = 0
         for k, l, st in self.ops:
-            if k in ("conv1", "conv", "deconv"):
+            if k in writers:
                 st["slot"] = n
                 n += 1
         self.guard = torch.zeros((2, max(n, 1)), dtype=torch.int32, device=dev)
@@ -550,7 +571,7 @@ class GpuNet:
             self._run_python_layer(l, T)
             return
         x = T[l.bottoms[0]]
-        if kind != "conv1" and not isinstance(x, H2):
+        if kind not in ("conv1", "conv_first") and not isinstance(x, H2):
             # a blob that arrived as fp32 NCHW (a Python layer's top, or a host-written blob of forward(start=))
             x = H2.from_nchw(x.to(self.device), fmt)
         if kind == "conv1":
@@ -558,6 +579,36 @@ class GpuNet:
             out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
             L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
                    s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+        elif kind == "conv_first":
+            n, _, h, w = x.shape
+            ho = (h + 2 * s["pad"] - s["k"]) // s["stride"] + 1
+            wo = (w + 2 * s["pad"] - s["k"]) // s["stride"] + 1
+            out = self._alloc_out(s["top"], n, ho, wo, s["cout"], fmt)
+            if out.c_off != 0 or out.c != out.ctot:
+                raise L.ShfError("conv %s writes into a concat window; not supported for the first convolution" % l.name)
+            L.call("shf_conv_first", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], s["k"],
+                   s["stride"], s["pad"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+        elif kind == "eltwise":
+            xs = [x]
+            for b in l.bottoms[1:]:
+                y = T[b]
+                xs.append(y if isinstance(y, H2) else H2.from_nchw(y.to(self.device), fmt))
+            for y in xs:
+                if (y.n, y.h, y.w, y.c) != (x.n, x.h, x.w, x.c) or y.fmt != x.fmt or y.c_off != 0 or y.c != y.ctot:
+                    raise L.ShfError("Eltwise %s: bottoms must be whole tensors of one shape and format" % l.name)
+            out = self._alloc_out(s["top"], x.n, x.h, x.w, x.c, fmt)
+            ptrs = (C.c_void_p * len(xs))(*[y.t.data_ptr() for y in xs])
+            coeff = (C.c_float * len(xs))(*s["coeff"])
+            L.call("shf_eltwise_sum", ptrs, coeff, len(xs), _ptr(out.t), x.n * x.h * x.w, x.c, out.ctot, out.c_off,
+                   int(s["relu"]), x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
+        elif kind == "conv" and s.get("stride", 1) != 1:
+            if x.c_off != 0 or x.c != x.ctot:
+                raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
+            sd = s["stride"]
+            out = self._alloc_out(s["top"], x.n, (x.h - 1) // sd + 1, (x.w - 1) // sd + 1, s["cout"], fmt)
+            wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
+            L.call("shf_conv_igemm_strided", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, sd, s["cin"],
+                   s["cout"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
         elif kind == "conv":
             if x.c_off != 0 or x.c != x.ctot:
                 raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
@@ -593,9 +644,19 @@ class GpuNet:
                 e1.record()
                 self.events.append((e0, e1))
         elif kind == "pool":
-            out = H2.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c, self.device, x.fmt)
+            if x.c_off != 0 or x.c != x.ctot:
+                raise L.ShfError("pool %s reads a channel window; not supported" % l.name)
+            lib = L.load()
+            anyp = 1 if (s["ph"] or s["pw"]) else 0
+            ho = lib.shf_pool_out_size(x.h, s["kh"], s["sh"], s["ph"], anyp)
+            wo = lib.shf_pool_out_size(x.w, s["kw"], s["sw"], s["pw"], anyp)
+            out = H2.empty(x.n, ho, wo, x.c, self.device, x.fmt)
             T[l.tops[0]] = out
-            L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, x.fmt, st)
+            if (s["kh"], s["kw"], s["sh"], s["sw"], s["ph"], s["pw"]) == (2, 2, 2, 2, 0, 0):
+                L.call("shf_maxpool2x2", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, x.fmt, st)
+            else:
+                L.call("shf_maxpool", _ptr(x.t), _ptr(out.t), x.n, x.h, x.w, x.c, s["kh"], s["kw"], s["sh"], s["sw"], s["ph"],
+                       s["pw"], x.fmt, st)
         elif kind == "deconv":
             ho = s["s"] * (x.h - 1) + s["k"] - 2 * s["pad"]
             wo = s["s"] * (x.w - 1) + s["k"] - 2 * s["pad"]

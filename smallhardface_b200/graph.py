@@ -22,7 +22,7 @@ from . import caffe_proto as cp
 TRAIN, TEST = 0, 1
 
 SUPPORTED = ("Input", "Convolution", "Deconvolution", "ReLU", "Pooling", "Concat", "Reshape",
-             "Softmax", "Python", "Split", "BatchNorm", "Scale")
+             "Softmax", "Python", "Split", "BatchNorm", "Scale", "Eltwise")
 
 
 @dataclass
@@ -230,6 +230,14 @@ class NetSpec:
                 if len(spec.bottoms) != 1 or int(q.axis) != 1 or int(q.num_axes) != 1:
                     raise ValueError("%s: only the per-channel Scale (one bottom, axis 1, num_axes 1) is supported" % l.name)
                 spec.p = dict(bias_term=bool(q.bias_term))
+            elif l.type == "Eltwise":                      # eltwise_layer.cpp:10-35
+                q = l.eltwise_param
+                coeff = [float(c) for c in q.coeff]
+                if coeff and len(coeff) != len(spec.bottoms):
+                    raise ValueError("Eltwise Layer takes one coefficient per bottom blob.")
+                if coeff and int(q.operation) == 0:
+                    raise ValueError("Eltwise layer only takes coefficients for summation.")
+                spec.p = dict(operation=int(q.operation), coeff=coeff or [1.0] * len(spec.bottoms))
             elif l.type == "Python":
                 q = l.python_param
                 spec.p = dict(module=q.module, layer=q.layer, param_str=q.param_str)
@@ -317,6 +325,11 @@ class NetSpec:
                         wo -= 1
                 out = (n, c, ho, wo)
             elif t in ("ReLU", "Softmax"):
+                out = bs[0]
+            elif t == "Eltwise":
+                for b in bs[1:]:
+                    if tuple(b) != tuple(bs[0]):                 # eltwise_layer.cpp:27-30
+                        raise ValueError("%s: bottom shapes differ (%s vs %s)" % (spec.name, bs[0], b))
                 out = bs[0]
             elif t in ("BatchNorm", "Scale"):
                 self.check_param_shape(spec, bs[0][1] if len(bs[0]) > 1 else 1)

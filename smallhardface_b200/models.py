@@ -170,3 +170,76 @@ def splice_dim_red(net: Msg) -> Msg:
     red.convolution_param.bias_filler.value = 0.0
     out.layer = layers[:split] + [red, relu_layer("conv4_fuse_final_dim_red_relu", "conv4_fuse_final")] + layers[split:]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ResNet-style backbone (BASELINE north_star names "the ResNet/VGG backbone"; the reference ships no ResNet prototxt,
+# SURVEY F1).  Layer naming and structure follow the public Caffe ResNet-50 deploy file (conv1 7x7/2 + bn + scale + relu,
+# pool1 MAX 3x3/2, bottleneck blocks res{2,3}{a,b,..}_branch{1,2a,2b,2c} with the stride on the FIRST 1x1 convolutions of
+# a stage, in-place BatchNorm(use_global_stats) / Scale(bias_term) / ReLU, Eltwise SUM + ReLU), cut after res3 (stride 8:
+# the stride of the reference's detection heads) and followed by the standard single-head tail of test_template.prototxt.
+# ---------------------------------------------------------------------------------------------------------------
+def _bn_scale(name: str, blob: str) -> List[Msg]:
+    return [
+        Msg("LayerParameter", name="bn" + name, type="BatchNorm", bottom=[blob], top=[blob],
+            batch_norm_param=Msg("BatchNormParameter", use_global_stats=True)),
+        Msg("LayerParameter", name="scale" + name, type="Scale", bottom=[blob], top=[blob],
+            scale_param=Msg("ScaleParameter", bias_term=True)),
+    ]
+
+
+def _res_conv(name, bottom, num_output, kernel, pad, stride) -> Msg:
+    c = Msg("ConvolutionParameter", num_output=num_output, bias_term=False)
+    c.pad = [pad]
+    c.kernel_size = [kernel]
+    c.stride = [stride]
+    return Msg("LayerParameter", name=name, type="Convolution", bottom=[bottom], top=[name], convolution_param=c)
+
+
+def _bottleneck(stage: int, block: str, bottom: str, mid: int, out: int, stride: int, project: bool) -> List[Msg]:
+    pre = "res%d%s" % (stage, block)
+    tag = "%d%s" % (stage, block)
+    layers: List[Msg] = []
+    shortcut = bottom
+    if project:
+        layers += [_res_conv(pre + "_branch1", bottom, out, 1, 0, stride)] + _bn_scale(tag + "_branch1", pre + "_branch1")
+        shortcut = pre + "_branch1"
+    layers += [_res_conv(pre + "_branch2a", bottom, mid, 1, 0, stride)] + _bn_scale(tag + "_branch2a", pre + "_branch2a")
+    layers.append(relu_layer(pre + "_branch2a_relu", pre + "_branch2a"))
+    layers += [_res_conv(pre + "_branch2b", pre + "_branch2a", mid, 3, 1, 1)] + _bn_scale(tag + "_branch2b", pre + "_branch2b")
+    layers.append(relu_layer(pre + "_branch2b_relu", pre + "_branch2b"))
+    layers += [_res_conv(pre + "_branch2c", pre + "_branch2b", out, 1, 0, 1)] + _bn_scale(tag + "_branch2c", pre + "_branch2c")
+    layers.append(Msg("LayerParameter", name=pre, type="Eltwise", bottom=[shortcut, pre + "_branch2c"], top=[pre]))
+    layers.append(relu_layer(pre + "_relu", pre))
+    return layers
+
+
+def build_resnet_test_net(blocks=(3, 4), input_hw=(224, 224)) -> Msg:
+    """ResNet-50 through res3 (``blocks`` = bottlenecks per stage) + the standard detection head."""
+    net = Msg("NetParameter", name="face_resnet")
+    net.input = ["data", "im_info"]
+    net.input_shape = [Msg("BlobShape", dim=[1, 3, int(input_hw[0]), int(input_hw[1])]), Msg("BlobShape", dim=[1, 3])]
+    layers = [_res_conv("conv1", "data", 64, 7, 3, 2)] + _bn_scale("_conv1", "conv1") + [relu_layer("conv1_relu", "conv1")]
+    layers.append(Msg("LayerParameter", name="pool1", type="Pooling", bottom=["conv1"], top=["pool1"],
+                      pooling_param=Msg("PoolingParameter", pool=0, kernel_size=3, stride=2)))
+    bottom = "pool1"
+    for si, n_blocks in enumerate(blocks):
+        stage = si + 2
+        mid, out = 64 << si, 256 << si
+        for bi in range(n_blocks):
+            block = "abcdefgh"[bi]
+            layers += _bottleneck(stage, block, bottom, mid, out, 2 if (bi == 0 and stage > 2) else 1, project=bi == 0)
+            bottom = "res%d%s" % (stage, block)
+    hp = lambda: [_param(1.0, 1.0), _param(2.0, 0)]
+    layers += [
+        conv_layer("head", bottom, "head", 128, 3, 1, hp(), stride=1),
+        relu_layer("head_relu", "head"),
+        conv_layer("cls_score", "head", "cls_score_output", 6, 1, 0, hp(), stride=1),
+        conv_layer("bbox_pred", "head", "bbox_pred_output", 12, 1, 0, hp(), stride=1),
+        Msg("LayerParameter", name="cls_reshape", type="Reshape", bottom=["cls_score_output"],
+            top=["cls_score_reshape_output"],
+            reshape_param=Msg("ReshapeParameter", shape=Msg("BlobShape", dim=[0, 2, -1, 0]))),
+    ]
+    layers += _tail("cls_score_reshape_output")
+    net.layer = layers
+    return net
