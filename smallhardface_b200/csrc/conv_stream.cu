@@ -384,17 +384,23 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const float scale = p.out_scale;
     const uint32_t drained0 = (CTAS == 2) ? mapa_shared(acc_empty(0), 0) : acc_empty(0);   // in the leader
     const uint32_t drained1 = (CTAS == 2) ? mapa_shared(acc_empty(1), 0) : acc_empty(1);
-    int gp = 0, tile_it = 0;
+    int gp = 0, tile_it = 0, last_nt = -1;
     float gmax = 0.f;                            // range guard: max |x| this thread has written
     for (int t = cta_lin; t < p.total_tiles; t += cta_cnt) {
       int nt, x0, y0, img;
       decode_tile(t, nt, x0, y0, img);
       // stage this tile's bias slice in shared memory now, so that its global-load latency hides behind the main loop
       // (read per 8-channel group straight from global memory it serialised ~16 L2 round trips into every epilogue)
+      // Layers with ONE channel tile (conv1_2) keep the same slice for every tile: it is staged once, and the eight warps
+      // are not forced back into lockstep by a barrier per tile (their drains / shuffles / stores then overlap freely).
+      if (nt != last_nt) {
+        ++tile_it;
+        float* bias_w = bias_s + (tile_it & 1) * BN;
+        if (w * 32 + lane < BN) bias_w[w * 32 + lane] = p.bias ? __ldg(p.bias + nt * BN + w * 32 + lane) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps only
+        last_nt = nt;
+      }
       float* bias_t = bias_s + (tile_it & 1) * BN;
-      if (w * 32 + lane < BN) bias_t[w * 32 + lane] = p.bias ? __ldg(p.bias + nt * BN + w * 32 + lane) : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // the eight epilogue warps only
-      ++tile_it;
       float acc[kCols];
 #pragma unroll
       for (int c = 0; c < kCols; ++c) acc[c] = 0.f;

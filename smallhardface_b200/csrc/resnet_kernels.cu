@@ -89,8 +89,7 @@ __global__ void __launch_bounds__(256) maxpool_h2_kernel(const __half* __restric
 
 // First convolution, 3 input channels, square K x K kernel, stride S, pad P, COUT = 64 output channels: fp32 FMAs.
 // A CTA owns a 16 x 8 tile of OUTPUT pixels: the fp32 input patch ((15 S + K) x (7 S + K) x 3) and the whole weight
-// tensor (3 K K x 64 floats, transposed to [tap][cout]) sit in shared memory; a thread accumulates the 64 channels of
-// one pixel: per tap one LDS of its input value and 16 broadcast LDS.128 of weights feed 64 FFMAs.
+// tensor (3 K K x 64 floats, transposed to [tap][cout]) sit in shared memory.
 constexpr int kCfTH = 16, kCfTW = 8, kCfThreads = 128, kCfCout = 64;
 __global__ void __launch_bounds__(kCfThreads) conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, __half* __restrict__ out,
@@ -106,7 +105,11 @@ __global__ void __launch_bounds__(kCfThreads) conv_first_kernel(const float* __r
     const int o = i % kCfCout, t = i / kCfCout;  // w is OIHW: (o, c, r, s) -> tap index t = (c * K + r) * K + s
     w_s[i] = __ldg(w + (size_t)o * taps + t);
   }
-  const int m = threadIdx.x, ly = m >> 3, lx = m & 7;
+  // thread = two horizontally adjacent output pixels x one half of the output channels (the half is warp-uniform, so the
+  // weight loads stay broadcasts): per tap 2 + 8 shared-memory loads feed 64 FFMAs
+  const int pair = threadIdx.x & 63, half = threadIdx.x >> 6;
+  const int ly = pair >> 2, lx = (pair & 3) * 2;
+  constexpr int kHalf = kCfCout / 2;
   const size_t out_plane = (size_t)N * HO * WO * kCfCout;
   float gmax = 0.f;
   const int total_tiles = tiles_x * tiles_y * N;
@@ -125,38 +128,47 @@ __global__ void __launch_bounds__(kCfThreads) conv_first_kernel(const float* __r
                      ? __ldg(in + (((size_t)img * 3 + c) * H + iy) * W + ix) : 0.f;      // zero padding
     }
     __syncthreads();
-    float acc[kCfCout];
+    float acc0[kHalf], acc1[kHalf];
 #pragma unroll
-    for (int o = 0; o < kCfCout; ++o) acc[o] = 0.f;
+    for (int o = 0; o < kHalf; ++o) { acc0[o] = 0.f; acc1[o] = 0.f; }
     const float* mine = patch + (ly * S) * pw + lx * S;
     for (int c = 0; c < 3; ++c)
       for (int r = 0; r < K; ++r)
         for (int s = 0; s < K; ++s) {
-          const float x = mine[(c * ph + r) * pw + s];
-          const float4* wt = reinterpret_cast<const float4*>(w_s + ((c * K + r) * K + s) * kCfCout);
+          const float xa = mine[(c * ph + r) * pw + s], xb = mine[(c * ph + r) * pw + s + S];
+          const float4* wt = reinterpret_cast<const float4*>(w_s + ((c * K + r) * K + s) * kCfCout + half * kHalf);
 #pragma unroll
-          for (int o4 = 0; o4 < kCfCout / 4; ++o4) {
+          for (int o4 = 0; o4 < kHalf / 4; ++o4) {
             const float4 w4 = wt[o4];
-            acc[4 * o4 + 0] = fmaf(x, w4.x, acc[4 * o4 + 0]);
-            acc[4 * o4 + 1] = fmaf(x, w4.y, acc[4 * o4 + 1]);
-            acc[4 * o4 + 2] = fmaf(x, w4.z, acc[4 * o4 + 2]);
-            acc[4 * o4 + 3] = fmaf(x, w4.w, acc[4 * o4 + 3]);
+            acc0[4 * o4 + 0] = fmaf(xa, w4.x, acc0[4 * o4 + 0]);
+            acc0[4 * o4 + 1] = fmaf(xa, w4.y, acc0[4 * o4 + 1]);
+            acc0[4 * o4 + 2] = fmaf(xa, w4.z, acc0[4 * o4 + 2]);
+            acc0[4 * o4 + 3] = fmaf(xa, w4.w, acc0[4 * o4 + 3]);
+            acc1[4 * o4 + 0] = fmaf(xb, w4.x, acc1[4 * o4 + 0]);
+            acc1[4 * o4 + 1] = fmaf(xb, w4.y, acc1[4 * o4 + 1]);
+            acc1[4 * o4 + 2] = fmaf(xb, w4.z, acc1[4 * o4 + 2]);
+            acc1[4 * o4 + 3] = fmaf(xb, w4.w, acc1[4 * o4 + 3]);
           }
         }
-    const int oy = y0 + ly, ox = x0 + lx;
-    if (oy < HO && ox < WO) {
-      __half* px = out + (((size_t)img * HO + oy) * WO + ox) * kCfCout;
+    const int oy = y0 + ly;
 #pragma unroll
-      for (int o8 = 0; o8 < kCfCout / 8; ++o8) {
-        float v[8];
+    for (int pxi = 0; pxi < 2; ++pxi) {
+      const int ox = x0 + lx + pxi;
+      if (oy < HO && ox < WO) {
+        __half* px = out + (((size_t)img * HO + oy) * WO + ox) * kCfCout;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float y = acc[8 * o8 + j] + (bias ? __ldg(bias + 8 * o8 + j) : 0.f);
-          if (relu) y = fmaxf(y, 0.f);
-          gmax = fmaxf(gmax, fabsf(y));
-          v[j] = y;
+        for (int o8 = 0; o8 < kHalf / 8; ++o8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y = (pxi ? acc1[8 * o8 + j] : acc0[8 * o8 + j]) + (bias ? __ldg(bias + half * kHalf + 8 * o8 + j) : 0.f);
+            if (relu) y = fmaxf(y, 0.f);
+            gmax = fmaxf(gmax, fabsf(y));
+            v[j] = y;
+          }
+          // hf8 rows are 64-channel blocks [64 x al8 | 64 x ah8]: 8-channel groups of either half land in the same block
+          act_store8(px, out_plane, half * kHalf + 8 * o8, v, out_fmt);
         }
-        act_store8(px, out_plane, 8 * o8, v, out_fmt);
       }
     }
   }

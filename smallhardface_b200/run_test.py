@@ -80,15 +80,28 @@ def inference(cfg, imdb, prototxt_path: str, start: int, end: int, thresh: float
     from .detector import Detector
     det = Detector(prototxt_path, cfg.TEST.MODEL, device, C.detect_config(cfg, thresh=thresh))
     all_boxes = [[[] for _ in range(end - start)] for _ in range(imdb.num_classes)]
-    for i0 in range(start, end, batch):
+    # with the conv stack on the GPU, `cv2.imread` (file read + JPEG / PNG decode on the host, lib/test.py:113)
+    # is the next ceiling.  The decode of batch i+1 runs on worker threads (OpenCV releases the GIL) while batch i is on the
+    # GPU; images reach the device as uint8 through page-locked staging (Detector.upload) and are resized there.
+    from concurrent.futures import ThreadPoolExecutor
+
+    def load(i0):
         paths = [imdb.image_path_at(i) for i in range(i0, min(i0 + batch, end))]
-        images = [cv2.imread(p) for p in paths]
-        for p, im in zip(paths, images):
-            if im is None:
-                raise IOError("cv2.imread failed on {}".format(p))
-        for j, d in enumerate(det.detect(images)):
-            all_boxes[1][i0 - start + j] = d
-        logger.info("im_detect: %d/%d", min(i0 + batch, end) - start, end - start)
+        return paths, list(pool.map(cv2.imread, paths))
+
+    starts = list(range(start, end, batch))
+    with ThreadPoolExecutor(max_workers=max(1, min(batch, os.cpu_count() or 1))) as pool, \
+            ThreadPoolExecutor(max_workers=1) as ahead:
+        nxt = ahead.submit(load, starts[0]) if starts else None
+        for k, i0 in enumerate(starts):
+            paths, images = nxt.result()
+            nxt = ahead.submit(load, starts[k + 1]) if k + 1 < len(starts) else None
+            for p, im in zip(paths, images):
+                if im is None:
+                    raise IOError("cv2.imread failed on {}".format(p))
+            for j, d in enumerate(det.detect(images)):
+                all_boxes[1][i0 - start + j] = d
+            logger.info("im_detect: %d/%d", min(i0 + batch, end) - start, end - start)
     return all_boxes
 
 

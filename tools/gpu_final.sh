@@ -1,7 +1,7 @@
 #!/bin/bash
 # Final 1-GPU evidence of the round: tests (+ the unmodified reference driver when _refdata/ is pushed), the launch list
 # and full captures of the shipped kernels, level tables, the bench line with BASELINE configs[4], the reference arm.
-T=r02
+T=${TAG:-r02f}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_gpu.txt 2>&1; nproc >> gpurun_out/${T}_gpu.txt
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 -rA 2>&1 | grep -v "^PASSED" | tail -100 > gpurun_out/${T}_pytest.log
@@ -23,6 +23,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv
    python tools/level_conv_only.py 2048 1 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:segmented_sort|mask_sweep|iou_mask|vote_reduce" -c 5 -f -o gpurun_out/${T}_post \
    python -c "import __graft_entry__ as g; g.smoke()" > /dev/null 2>&1
+timeout 300 python tools/time_conv1.py 2048 1 1 > gpurun_out/${T}_conv1_tc_time.txt 2>&1; timeout 300 python tools/time_conv1.py 1408 16 1 >> gpurun_out/${T}_conv1_tc_time.txt 2>&1
+timeout 300 python tools/plugin_breakdown.py 2>&1 | tail -7 > gpurun_out/${T}_plugin_breakdown.txt
+timeout 300 python tools/resnet_level.py 1408 1 2>&1 | tail -16 > gpurun_out/${T}_resnet_level1408.txt
 timeout 1200 python bench.py --steps 10 --warmup 3 --wider-shaped 3226 > gpurun_out/${T}_bench_1gpu.json 2> gpurun_out/${T}_bench.err
 tail -c 600 gpurun_out/${T}_bench_1gpu.json
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err
