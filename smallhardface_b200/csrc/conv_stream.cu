@@ -623,6 +623,9 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   p.tiles_y = (H + kTH - 1) / kTH;
   p.n_tiles = cout / bn;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * batch;
+  // Accumulator drain period in 64-channel chunks: one (36 k-steps) for 3x3 kernels.  Four chunks on the fast format
+  // measured 1-2 % faster in a same-box probe (profiles/r02f_probe_g.txt) but add ~1e-6 of accumulator truncation, which
+  // the hf8 operand-model test (3e-6) does not allow: not taken.
   p.chunks_per_phase = (p.taps == 9) ? 1 : 9;
   if (const char* e = shf_probe_env("SHF_PROBE_G")) { int v = atoi(e); if (v >= 1) p.chunks_per_phase = v; }
   p.ctot = out_channels_total;
