@@ -7,7 +7,7 @@ per-pass ``caffe.Net.forward`` loop.
         --amend DATA_DIR <images> TEST.DB general_png TEST.MODEL <caffemodel> TEST.GPU_ID "[0]"
 
 Under ``torchrun`` every rank takes the reference's contiguous shard (``lib/test.py:329-335``) and the boxes are
-exchanged with the path's one all-gather (``parallel.py``); rank 0 writes the files.  The unmodified reference driver
+exchanged with the path's one all-gather (``parallel.py``, after a scalar all-reduce that sizes it); rank 0 writes the files.  The unmodified reference driver
 on the drop-in ``caffe`` module is ``tools/run_reference_driver.py``; this module is the variant that keeps images and
 detections on the GPU between the layers the reference round-trips through NumPy.
 
@@ -126,9 +126,7 @@ def test_net(cfg, imdb, output_dir: str, target_test: str, thresh: float = 0.05,
         dev = "cuda:%d" % (int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else _first_gpu(cfg))
         mine = inference(cfg, imdb, target_test, a, b, thresh, batch, dev)
         if world > 1:
-            parts = [None] * world
-            dist.all_gather_object(parts, mine[1])          # variable-length float64 rows: the object gather of the CLI
-            dets = [[[] for _ in range(len(imdb))], [d for part in parts for d in part]]
+            dets = [[[] for _ in range(len(imdb))], gather_all(mine[1], len(imdb), world, torch.device(dev))]
         else:
             dets = mine
         assert len(dets[1]) == len(imdb), "Detection result compromised"
@@ -140,6 +138,26 @@ def test_net(cfg, imdb, output_dir: str, target_test: str, thresh: float = 0.05,
         logger.info(result)
     del torch
     return dets, result
+
+
+def gather_all(local_dets, n_images: int, world: int, device):
+    """Every rank's per-image (M, 5) results -> the full rank-ordered list on every rank (``lib/test.py:336-344``): a scalar
+    all-reduce sizes the payload, then the path's ONE all-gather of packed (count | boxes) blocks (``parallel.py``).  Rows
+    travel as float32 -- what the device produced (``Detector.download`` widens to float64 afterwards)."""
+    import torch
+    import torch.distributed as dist
+    from .parallel import gather_detections, merge_gathered
+    per = int(np.ceil(1.0 * n_images / world))
+    rows = torch.tensor([max([len(d) for d in local_dets] + [1])], dtype=torch.int64, device=device)
+    dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+    rows = int(rows.item())
+    buf = torch.zeros((per, rows, 5), dtype=torch.float32)
+    cnt = torch.zeros((per,), dtype=torch.int32)
+    for j, d in enumerate(local_dets):
+        buf[j, :len(d)] = torch.from_numpy(np.asarray(d, dtype=np.float32).reshape(-1, 5))
+        cnt[j] = len(d)
+    merged = merge_gathered(gather_detections(buf.to(device), cnt.to(device), world, rows=rows), n_images, world)
+    return [m.astype(local_dets[0].dtype) if len(local_dets) else m for m in merged]
 
 
 def _first_gpu(cfg) -> int:

@@ -73,3 +73,28 @@ def test_two_rank_all_gather_reproduces_single_process_order(tmp_path, n_images)
     for idx, got in enumerate(merged):
         d, n = _fake_result(idx)
         assert np.array_equal(got, d[:n])
+
+
+def _cli_worker(rank, world, port, n_images, out_dir):
+    """run_test.gather_all: the CLI's exchange of variable-length per-image results (float64 rows from box voting)."""
+    from smallhardface_b200.run_test import gather_all
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_range(n_images, world, rank)
+    local = []
+    for idx in range(a, b):
+        d, n = _fake_result(idx, cap=40)
+        local.append(d[:n].astype(np.float64))
+    merged = gather_all(local, n_images, world, torch.device("cpu"))
+    assert len(merged) == n_images
+    for idx, got in enumerate(merged):
+        d, n = _fake_result(idx, cap=40)
+        assert got.dtype == np.float64 and np.array_equal(got, d[:n].astype(np.float64)), idx
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [3, 7])
+def test_cli_gather_all_two_ranks(tmp_path, n_images):
+    mp.spawn(_cli_worker, args=(2, _free_port(), n_images, str(tmp_path)), nprocs=2, join=True)

@@ -214,3 +214,48 @@ def test_resnet_detector_pyramid_fast_format(tmp_path):
     ws, wb = match_rows(raw[:, :4], raw[:, 4], ref[:, :4], ref[:, 4])
     print("resnet detector: %d raw rows (ref %d), %d voted; worst score err %.2e, box err %.2e px" % (len(raw), len(ref), len(got), ws, wb))
     assert len(ref) > 20 and ws < SCORE_TOL and wb < BOX_TOL
+
+
+@needs_gpu
+@pytest.mark.skipif(not HAVE_GPU, reason="no CUDA device")
+def test_resnet_through_the_caffe_net_surface(tmp_path):
+    """The ResNet deployment through the drop-in `caffe.Net` (plugin path: CUDA graph per level shape -- first forward
+    captures, second replays), driven like lib/test.py:21-66, both passes of two pyramid levels against the oracle."""
+    from oracle import detect as OD
+    from oracle import preprocess as OPRE
+    from smallhardface_b200 import compat
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_net import BOX_TOL, SCORE_TOL, match_rows
+    compat.install()
+    import caffe
+    proto, model = deploy.write_synthetic_resnet_deployment(str(tmp_path), blocks=(3, 4))
+    caffe.set_mode_gpu()
+    caffe.set_device(0)
+    net = caffe.Net(str(proto), str(model), caffe.TEST)
+    assert net.outputs == ["boxes", "cls_prob"] and "res3d" in net.blobs and net.params["conv1"][0].data.shape == (64, 3, 7, 7)
+    onet = IndepNet(proto, model, engine="torch")
+    im = deploy.synthetic_image(9, (120, 168))
+    scales = OPRE.pyramid_scales(im.shape, (300, 800))
+    worst = 0.0
+    for rep in range(2):                                   # 0: graph capture, 1: replay
+        for blob, s in zip(OPRE.get_image_blobs(im, scales), scales):
+            for flip in (False, True):
+                d = np.ascontiguousarray(blob[..., ::-1]) if flip else blob
+                h, w = d.shape[2:]
+                nh, nw = -(-h // 16) * 16, -(-w // 16) * 16
+                data = np.pad(d, ((0, 0), (0, 0), (0, nh - h), (0, nw - w)), "constant").astype(F32)
+                info = np.array([[h, w, s]], F32)
+                net.blobs["data"].reshape(*data.shape)
+                net.blobs["im_info"].reshape(*info.shape)
+                out = net.forward(data=data, im_info=info)
+                if flip:
+                    out["boxes"][:, [1, 3]] = w - out["boxes"][:, [3, 1]]
+                boxes = net.blobs["boxes"].data[:, 1:5] / s
+                probs = net.blobs["cls_prob"].data
+                rp, rb = OD.forward_level(onet, d, s, flip)
+                ws, wb = match_rows(boxes, probs[:, 1], rb[:, :4], rp[:, 1])
+                assert ws < SCORE_TOL and wb < BOX_TOL, (rep, s, flip, ws, wb)
+                worst = max(worst, wb)
+    got = net.blobs["res2c"].data                           # an intermediate blob through the lazy device->host sync
+    assert got.shape == onet.blobs["res2c"].shape and relerr(got, onet.blobs["res2c"]) < 5e-4
+    print("resnet through caffe.Net: worst box error %.2e raw px" % worst)
