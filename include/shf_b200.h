@@ -65,6 +65,15 @@ int shf_conv_igemm_strided(const void* in_h2, const void* w_h2, const float* bia
                            int stride, int cin, int cout, int out_channels_total, int out_channel_offset, float out_scale,
                            int relu, int in_format, int out_format, unsigned int* range_guard, void* stream);
 
+/* shf_conv_igemm with the residual add of a ResNet block fused into the epilogue (EltwiseLayer SUM with unit coefficients,
+ * eltwise_layer.cpp:52-57, then the block's in-place ReLU): out = [relu](conv(in) * out_scale + bias + residual).  residual
+ * [dev]: an activation tensor of the same N x H x W with res_channels_total channels, read at res_channel_offset, in
+ * res_format.  The branch output is never written to HBM. */
+int shf_conv_igemm_res(const void* in_h2, const void* w_h2, const float* bias, const void* residual, void* out_h2, int batch,
+                       int H, int W, int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
+                       int res_channels_total, int res_channel_offset, float out_scale, int relu, int in_format, int res_format,
+                       int out_format, unsigned int* range_guard, void* stream);
+
 /* ---- layers a ResNet-style backbone adds (BASELINE north_star names "the ResNet/VGG backbone"; csrc/resnet_kernels.cu) -- */
 /* EltwiseLayer SUM (eltwise_layer.cpp:37-77): out = sum_t coeffs[t] * ins[t] over n_in (<= 4) activation tensors of
  * `pixels` x C [dev; ins is a HOST array of device pointers], coeffs [host, may be NULL = all 1], optionally followed by the

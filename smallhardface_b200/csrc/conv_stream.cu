@@ -63,6 +63,11 @@ struct StreamParams {
   long long pool_plane_elems;
   int pool_ctot, pool_coffset;
   unsigned int* guard;        // range guard slot (max |x| written, float bits) or nullptr
+  // fused residual add (EltwiseLayer SUM with unit coefficients, eltwise_layer.cpp:52-57) before the ReLU: the shortcut
+  // tensor of a ResNet block, same N x H x W, read at a channel offset like the output is written
+  const __half* res;          // nullptr: none
+  long long res_plane_elems;
+  int res_ctot, res_coffset, res_fmt;
 };
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -76,7 +81,9 @@ constexpr bool kProbes = false;               // product builds: the timing prob
 // FMT = operand format of the activations read AND of the packed weights (SHF_FMT_*): a template parameter so that the
 // MMA-issuing thread's loop carries no format / probe / residency tests (r02: ncu showed that thread, at ~110 SASS
 // instructions and 550 cycles per 8-MMA weight stage, pacing every layer -- the N = 64 ones at half the tensor rate).
-template <int BN, int CTAS, int FMT>
+// RES = the launch adds a residual tensor in its epilogue (ResNet blocks): an instantiation of its own, so that the staged
+// row loads do not cost the VGG path registers (the 128-wide variants sit at the 168-register cap).
+template <int BN, int CTAS, int FMT, bool RES = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const StreamParams p) {
@@ -447,9 +454,21 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool post_pool = p.pool_out && !p.out;
       if (!post_pool) {
 #pragma unroll
-        for (int c = 0; c < kCols; ++c) {
-          acc[c] = fmaf(acc[c], scale, bias_t[col0 + c]);
-          if (p.relu) acc[c] = fmaxf(acc[c], 0.f);
+        for (int c = 0; c < kCols; ++c) acc[c] = fmaf(acc[c], scale, bias_t[col0 + c]);
+        if (RES && p.res != nullptr) {                        // warp-uniform: all lanes take part in the staged row loads
+          const int ry = y0 + quad * 4;
+          const __half* rbase = p.res + (((size_t)img * p.H + ry) * p.W + x0) * (size_t)p.res_ctot;
+          const uint32_t rpitch = (uint32_t)p.W * (uint32_t)p.res_ctot, rct = (uint32_t)p.res_ctot;
+          auto src = [&](int row) -> const __half* {
+            const int dy = row >> 3, dx = row & 7;
+            return (ry + dy < p.H && x0 + dx < p.W) ? rbase + ((uint32_t)dy * rpitch + (uint32_t)dx * rct) : nullptr;
+          };
+          add_rows_in<kCols>(stage_s + w * 4096, lane, acc, p.res_fmt, p.res_coffset + nt * BN + col0,
+                             (size_t)p.res_plane_elems, src);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int c = 0; c < kCols; ++c) acc[c] = fmaxf(acc[c], 0.f);
         }
         if (p.guard && inside) {
 #pragma unroll
@@ -504,18 +523,18 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
-template <int BN, int CTAS, int FMT>
+template <int BN, int CTAS, int FMT, bool RES = false>
 int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
                   cudaStream_t stream) {
   static bool attr[64] = {};                   // function attributes are per device
   int dev = 0;
   SHF_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr[dev]) {
-    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS, FMT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   if (CTAS == 1) {
-    conv_stream_kernel<BN, CTAS, FMT><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    conv_stream_kernel<BN, CTAS, FMT, RES><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -529,7 +548,7 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamPara
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS, FMT>, ta, tb, p));
+    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS, FMT, RES>, ta, tb, p));
   }
   SHF_LAUNCH_CHECK();
   return 0;
@@ -554,7 +573,8 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
                          int cin, int cout, int ksize, int dilation, int out_channels_total, int out_channel_offset,
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
                          int ctas, int in_format, int out_format, unsigned int* range_guard, void* stream,
-                         int in_stride = 1, int in_H = 0, int in_W = 0) {
+                         int in_stride = 1, int in_H = 0, int in_W = 0, const void* residual = nullptr,
+                         int res_channels_total = 0, int res_channel_offset = 0, int res_format = 0) {
   // in_stride > 1 (1x1 kernels only): H x W are the OUTPUT dims, the activations are read through a strided TMA view
   // of the in_H x in_W input (every in_stride-th pixel) -- conv_layer.cpp:8-28 with kernel 1, pad 0
   SHF_REQUIRE(ctas == 1 || ctas == 2, "shf_conv_igemm: %d CTAs per tile group", ctas);
@@ -567,6 +587,14 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
                     (!pool_out_h2 || (pool_channel_offset % 64 == 0 && pool_channels_total % 64 == 0)),
                 "shf_conv_igemm: hf8 tensors need channel windows aligned to 64");
   SHF_REQUIRE(out_h2 != nullptr || pool_out_h2 != nullptr, "shf_conv_igemm: no destination");
+  if (residual != nullptr) {
+    SHF_REQUIRE(pool_out_h2 == nullptr && out_h2 != nullptr, "shf_conv_igemm_res: no fused pooling with a residual");
+    SHF_REQUIRE(res_format == SHF_FMT_H2 || res_format == SHF_FMT_HF8, "shf_conv_igemm_res: unknown residual format %d", res_format);
+    SHF_REQUIRE(res_channel_offset % 8 == 0 && res_channels_total % 8 == 0 && res_channel_offset + cout <= res_channels_total &&
+                    (res_format == SHF_FMT_H2 || (res_channel_offset % 64 == 0 && res_channels_total % 64 == 0)),
+                "shf_conv_igemm_res: bad residual channel window [%d,%d) of %d", res_channel_offset,
+                res_channel_offset + cout, res_channels_total);
+  }
   if (pool_out_h2)
     SHF_REQUIRE(H % 2 == 0 && W % 2 == 0 && pool_channel_offset % 8 == 0 && pool_channels_total % 8 == 0 &&
                     pool_channel_offset + cout <= pool_channels_total,
@@ -579,6 +607,7 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
               "shf_conv_igemm: bad destination channel window [%d,%d) of %d", out_channel_offset,
               out_channel_offset + cout, out_channels_total);
   SHF_REQUIRE(batch >= 1 && H >= 1 && W >= 1 && dilation >= 1 && dilation <= 4, "shf_conv_igemm: bad geometry");
+  SHF_REQUIRE((long long)W * res_channels_total < (1ll << 29), "shf_conv_igemm_res: residual row overflows 32-bit offsets");
   SHF_REQUIRE((long long)W * out_channels_total < (1ll << 29) && (long long)W * pool_channels_total < (1ll << 29),
               "shf_conv_igemm: a row of %d pixels x %d channels overflows the epilogue's 32-bit in-tile offsets", W,
               out_channels_total);
@@ -652,6 +681,11 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   p.pool_ctot = pool_channels_total;
   p.pool_coffset = pool_channel_offset;
   p.guard = range_guard;
+  p.res = reinterpret_cast<const __half*>(residual);
+  p.res_plane_elems = (long long)batch * H * W * res_channels_total;
+  p.res_ctot = res_channels_total;
+  p.res_coffset = res_channel_offset;
+  p.res_fmt = res_format;
   const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 1536 + 8 * 4096;
 
   CUtensorMap ta, tb;
@@ -675,6 +709,13 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   const int grid = (p.total_tiles < groups ? p.total_tiles : groups) * ctas;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool f8 = in_format == SHF_FMT_HF8;
+  if (p.res != nullptr) {
+    SHF_REQUIRE(ctas == 2, "shf_conv_igemm_res: the residual epilogue exists for the CTA-pair kernel only");
+    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8, true>(ta, tb, p, smem_bytes, grid, st)
+                             : launch_stream<128, 2, SHF_FMT_H2, true>(ta, tb, p, smem_bytes, grid, st);
+    return f8 ? launch_stream<64, 2, SHF_FMT_HF8, true>(ta, tb, p, smem_bytes, grid, st)
+              : launch_stream<64, 2, SHF_FMT_H2, true>(ta, tb, p, smem_bytes, grid, st);
+  }
   if (ctas == 2) {
     if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
                              : launch_stream<128, 2, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
@@ -731,4 +772,17 @@ extern "C" int shf_conv_igemm_strided(const void* in_h2, const void* w_h2, const
   return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, HO, WO, cin, cout, 1, 1, out_channels_total,
                               out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_ctas, in_format, out_format,
                               range_guard, stream, stride, H, W);
+}
+
+// shf_conv_igemm + the residual add of a ResNet block in the epilogue: out = [relu](conv(in) * scale + bias + residual).
+// Replaces Convolution (+ BatchNorm + Scale) -> Eltwise SUM (-> ReLU) without writing and re-reading the branch output.
+extern "C" int shf_conv_igemm_res(const void* in_h2, const void* w_h2, const float* bias, const void* residual, void* out_h2,
+                                  int batch, int H, int W, int cin, int cout, int ksize, int dilation, int out_channels_total,
+                                  int out_channel_offset, int res_channels_total, int res_channel_offset, float out_scale,
+                                  int relu, int in_format, int res_format, int out_format, unsigned int* range_guard,
+                                  void* stream) {
+  SHF_REQUIRE(residual != nullptr, "shf_conv_igemm_res: residual is NULL");
+  return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
+                              out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_ctas, in_format, out_format,
+                              range_guard, stream, 1, 0, 0, residual, res_channels_total, res_channel_offset, res_format);
 }

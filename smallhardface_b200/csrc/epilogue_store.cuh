@@ -124,6 +124,83 @@ SHF_DEVICE void store_plane(uint8_t* stg, int lane, const float (&v)[KC], int pl
   __syncwarp();
 }
 
+// Mirror image of copy_rows_out: fetch NR rows of one plane into the staging buffer, consecutive lanes on consecutive
+// 16 bytes of a row (rows outside the image are filled with zeros).
+template <int KC, int NR, typename SrcFn>
+SHF_DEVICE void copy_rows_in(uint8_t* stg, int lane, int plane, int fmt, int c_first, size_t plane_elems, SrcFn src_px) {
+  using RS = RowStore<KC>;
+  constexpr int kIters = NR * RS::kChunks / 32;
+  constexpr int kRowStep = 32 / RS::kChunks;
+  const int k = lane % RS::kChunks, r0 = lane / RS::kChunks;
+  size_t off;
+  if (plane == 0) {
+    off = (size_t)(c_first + 8 * k);
+  } else if (fmt == SHF_FMT_H2) {
+    off = plane_elems + (size_t)(c_first + 8 * k);
+  } else {
+    const int half = k / (KC / 16), kk = k % (KC / 16);
+    off = plane_elems + (size_t)((hf8_off(c_first) + half * 64 + kk * 16) >> 1);
+  }
+#pragma unroll
+  for (int j = 0; j < kIters; ++j) {
+    const int row = r0 + j * kRowStep;
+    const __half* px = src_px(row);
+    const uint4 v = px != nullptr ? __ldg(reinterpret_cast<const uint4*>(px + off)) : make_uint4(0u, 0u, 0u, 0u);
+    RS::put(stg, row, k, v);
+  }
+}
+
+// v[0, KC) += the values of this lane's pixel (staging row `lane`) of an activation tensor in format `fmt`: the residual
+// add of a ResNet block inside the conv epilogue.  Rows travel through the staging buffer like the stores do, so the
+// global loads are whole 128-byte (64-byte for KC = 32) rows per pixel instead of 16 bytes per lane and instruction.
+template <int KC, typename SrcFn>
+SHF_DEVICE void add_rows_in(uint8_t* stg, int lane, float (&v)[KC], int fmt, int c_first, size_t plane_elems, SrcFn src_px) {
+  using RS = RowStore<KC>;
+  copy_rows_in<KC, 32>(stg, lane, 0, fmt, c_first, plane_elems, src_px);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < KC / 8; ++k) {
+    const uint4 q = RS::get(stg, lane, k);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      v[8 * k + 2 * e] += f.x;
+      v[8 * k + 2 * e + 1] += f.y;
+    }
+  }
+  __syncwarp();
+  copy_rows_in<KC, 32>(stg, lane, 1, fmt, c_first, plane_elems, src_px);
+  __syncwarp();
+  if (fmt == SHF_FMT_H2) {
+#pragma unroll
+    for (int k = 0; k < KC / 8; ++k) {
+      const uint4 q = RS::get(stg, lane, k);
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        v[8 * k + 2 * e] += f.x;
+        v[8 * k + 2 * e + 1] += f.y;
+      }
+    }
+  } else {                                                   // chunks [0, KC/16): al8 of 16 channels each; the ah8 twins are not needed
+#pragma unroll
+    for (int k = 0; k < KC / 16; ++k) {
+      const uint4 q = RS::get(stg, lane, k);
+      const uint16_t* b2 = reinterpret_cast<const uint16_t*>(&q);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const __half2_raw r2 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)b2[e], __NV_E4M3);
+        const float2 f = __half22float2(__half2(r2));
+        v[16 * k + 2 * e] = fmaf(f.x, kHf8AlInv, v[16 * k + 2 * e]);
+        v[16 * k + 2 * e + 1] = fmaf(f.y, kHf8AlInv, v[16 * k + 2 * e + 1]);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // Fused 2x2 / stride-2 max pooling (pooling_layer.cpp:140-187) of a warp's 4 x 8 pixel patch (lane = y * 8 + x), then
 // the same staged store for the 2 x 4 pooled pixels.  The four lanes of a window (l, l^1, l^8, l^9) SPLIT the channels
 // while they reduce: the x-exchange leaves each lane with the pair maximum of one half of the channels, the y-exchange

@@ -358,6 +358,22 @@ class GpuNet:
                 top = l.tops[0]
                 relu = (i + 1 < len(layers) and layers[i + 1].type == "ReLU" and layers[i + 1].bottoms == [top]
                         and layers[i + 1].tops == [top] and layers[i + 1].p["negative_slope"] == 0.0)
+                # shortcut + branch where the branch is the convolution launched just before (res*_branch2c, no ReLU of its
+                # own, read by nobody else): the add and the block's ReLU move into that launch's epilogue and the branch
+                # tensor never goes to HBM.  (fuse_pool=False / SHF_MATERIALIZE_ALL keep every blob readable.)
+                prev = self.ops[-1] if self.ops else None
+                if (self.fuse_pool and prev is not None and prev[0] == "conv" and len(l.bottoms) == 2
+                        and l.p["coeff"] == [1.0, 1.0] and prev[2]["top"] in l.bottoms and l.bottoms[0] != l.bottoms[1]
+                        and not prev[2]["relu"] and prev[2].get("stride", 1) == 1 and "pool_top" not in prev[2]
+                        and prev[2]["top"] not in self.concat_dst and len(consumers.get(prev[2]["top"], [])) == 1):
+                    st_prev = prev[2]
+                    self.fused_blobs.add(st_prev["top"])
+                    st_prev["residual"] = [b for b in l.bottoms if b != st_prev["top"]][0]
+                    st_prev["relu"] = relu
+                    st_prev["top"] = top
+                    st_prev["absorbed_eltwise"] = l.name
+                    i += 2 if relu else 1
+                    continue
                 self.ops.append(("eltwise", l, dict(relu=relu, coeff=[float(c) for c in l.p["coeff"]], top=top)))
                 i += 2 if relu else 1
                 continue
@@ -609,6 +625,27 @@ class GpuNet:
             wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
             L.call("shf_conv_igemm_strided", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, sd, s["cin"],
                    s["cout"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
+        elif kind == "conv" and "residual" in s:
+            if x.c_off != 0 or x.c != x.ctot:
+                raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
+            r = T[s["residual"]]
+            if not isinstance(r, H2):
+                r = H2.from_nchw(r.to(self.device), fmt)
+            if (r.n, r.h, r.w, r.c) != (x.n, x.h, x.w, s["cout"]):
+                raise L.ShfError("conv %s: residual %s has shape %s, the output %s" %
+                                 (l.name, s["residual"], (r.n, r.c, r.h, r.w), (x.n, s["cout"], x.h, x.w)))
+            out = self._alloc_out(s["top"], x.n, x.h, x.w, s["cout"], fmt)
+            wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
+            if self.profile:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            L.call("shf_conv_igemm_res", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(r.t), _ptr(out.t), x.n, x.h, x.w, s["cin"],
+                   s["cout"], s["k"], s["dil"], out.ctot, out.c_off, r.ctot, r.c_off, s["scale"], int(s["relu"]), x.fmt, r.fmt,
+                   out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            if self.profile:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.events.append((e0, e1))
         elif kind == "conv":
             if x.c_off != 0 or x.c != x.ctot:
                 raise L.ShfError("conv %s reads a channel window; not supported" % l.name)
@@ -695,7 +732,7 @@ class GpuNet:
                              "or run the whole net")
         idx_of = {n: i for i, n in enumerate(names)}
         first = [idx_of[l.name] for _, l, _ in self.ops]
-        absorbed = ("ReLU", "Pooling", "BatchNorm", "Scale")      # what a conv launch may have swallowed after itself
+        absorbed = ("ReLU", "Pooling", "BatchNorm", "Scale", "Eltwise")   # what a conv launch may have swallowed after itself
         op_layers = []
         for oi, f in enumerate(first):
             nxt = first[oi + 1] if oi + 1 < len(first) else len(names)

@@ -161,17 +161,41 @@ def test_strided_1x1_conv_matches_oracle(cin, cout, H, W, s, fmt):
 
 @needs_gpu
 @pytest.mark.skipif(not HAVE_GPU, reason="no CUDA device")
-@pytest.mark.parametrize("hw", [(224, 224), (150, 202)])
-def test_resnet_net_forward_matches_oracle(tmp_path, hw):
+@pytest.mark.parametrize("cin,cout,k,H,W,fmt,relu", [(64, 256, 1, 20, 28, 0, 1), (512, 128, 1, 9, 13, 1, 1), (128, 128, 3, 17, 24, 0, 0),
+                                                    (256, 64, 1, 16, 16, 1, 1)])
+def test_conv_with_fused_residual_matches_oracle(cin, cout, k, H, W, fmt, relu):
+    """shf_conv_igemm_res: conv * scale + bias + shortcut (+ ReLU) in one launch vs conv -> Eltwise SUM -> ReLU of the oracle."""
+    rng = np.random.RandomState(cin + cout + H)
+    x = (rng.randn(2, cin, H, W) * 20).astype(F32)
+    w = (rng.randn(cout, cin, k, k) * np.sqrt(2.0 / (cin * k * k))).astype(F32)
+    b = (rng.randn(cout) * 0.05).astype(F32)
+    res = (rng.randn(2, cout, H, W) * 30).astype(F32)
+    hx, hr = H2.from_nchw(dev(x), fmt), H2.from_nchw(dev(res), fmt)
+    ref = OL.eltwise_sum([hr.to_nchw().cpu().numpy(), OL.conv(hx.to_nchw().cpu().numpy(), w, b, pad=(k // 2, k // 2))])
+    if relu:
+        ref = OL.relu(ref)
+    packed, kexp = (pack_conv_weights_hf8 if fmt else pack_conv_weights)(w)
+    out = H2.empty(2, H, W, cout, DEV, fmt)
+    L.call("shf_conv_igemm_res", _ptr(hx.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(hr.t), _ptr(out.t), 2, H, W, cin, cout, k, 1,
+           cout, 0, cout, 0, float(2.0 ** -kexp), relu, fmt, fmt, fmt, None, _stream())
+    assert relerr(out.to_nchw().cpu().numpy(), ref) < (3e-6 if fmt == 0 else 3e-4)
+
+
+@needs_gpu
+@pytest.mark.skipif(not HAVE_GPU, reason="no CUDA device")
+@pytest.mark.parametrize("hw,fuse", [((224, 224), True), ((150, 202), True), ((150, 202), False)])
+def test_resnet_net_forward_matches_oracle(tmp_path, hw, fuse):
     """ResNet-50 through res3 + the standard detection head: every residual stage and the outputs against the independent
-    oracle reading; BASELINE tolerances (scores 1e-3, boxes 1e-2 px)."""
+    oracle reading; BASELINE tolerances (scores 1e-3, boxes 1e-2 px).  fuse: residual adds inside the branch2c conv
+    launches (the default) or as Eltwise launches of their own."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_gpu_net import BOX_TOL, SCORE_TOL, match_rows
     proto, model = deploy.write_synthetic_resnet_deployment(str(tmp_path), blocks=(3, 4), input_hw=hw)
     spec = NetSpec(cp.read_net_text(proto))
-    gnet = GpuNet(spec, load_weights(spec, cp.read_net_binary(model)), "cuda:0", fast_min_scale=None)
+    gnet = GpuNet(spec, load_weights(spec, cp.read_net_binary(model)), "cuda:0", fast_min_scale=None, fuse_pool=fuse)
     kinds = [k for k, _, _ in gnet.ops]
-    assert kinds.count("eltwise") == 7 and kinds.count("conv_first") == 1 and "pool" in kinds
+    assert kinds.count("eltwise") == (0 if fuse else 7) and sum(1 for _, _, s in gnet.ops if "residual" in s) == (7 if fuse else 0)
+    assert kinds.count("conv_first") == 1 and "pool" in kinds
     assert sum(1 for k, _, s in gnet.ops if k == "conv" and s["stride"] == 2) == 2          # res3a_branch1 / _branch2a
     onet = IndepNet(proto, model, engine="torch")
     data, info = _data(*hw), np.array([[hw[0], hw[1], 1.0]], F32)
