@@ -74,11 +74,13 @@ def get_imdb(cfg, name: str):
     raise KeyError("Unknown dataset: {}".format(name))
 
 
-def inference(cfg, imdb, prototxt_path: str, start: int, end: int, thresh: float = 0.05, batch: int = 8, device="cuda:0"):
-    """``lib/test.py:220-267`` inference_worker for images [start, end): returns ``all_boxes[class][image]``."""
+def inference(cfg, imdb, prototxt_path: str, start: int, end: int, thresh: float = 0.05, batch: int = 8, device="cuda:0",
+              detector=None):
+    """``lib/test.py:220-267`` inference_worker for images [start, end): returns ``all_boxes[class][image]``.
+    ``detector``: reuse a built ``Detector`` (weights loaded and packed) instead of constructing one."""
     import cv2
     from .detector import Detector
-    det = Detector(prototxt_path, cfg.TEST.MODEL, device, C.detect_config(cfg, thresh=thresh))
+    det = detector or Detector(prototxt_path, cfg.TEST.MODEL, device, C.detect_config(cfg, thresh=thresh))
     all_boxes = [[[] for _ in range(end - start)] for _ in range(imdb.num_classes)]
     # SURVEY 8f.1: with the conv stack on the GPU, `cv2.imread` (file read + JPEG / PNG decode on the host, lib/test.py:113)
     # is the next ceiling.  The decode of batch i+1 runs on worker threads (OpenCV releases the GIL) while batch i is on the
