@@ -12,8 +12,9 @@ on the drop-in ``caffe`` module is ``tools/run_reference_driver.py``; this modul
 detections on the GPU between the layers the reference round-trips through NumPy.
 
 Datasets: the ``general_<ext>`` loader (``lib/datasets/general.py:19-79``: every ``*.<ext>`` under ``DATA_DIR``, results as
-text files under the output directory).  The WIDER / FDDB / AFW / PASCAL loaders need their annotation files and are out
-of scope (SURVEY section 2 OUT); their result format is the same writer (``writers.write_detections``).
+text files under the output directory) and ``wider_{train,val,test}`` (``lib/datasets/wider.py``: image list from the
+annotation file, result files, the WIDER toolbox evaluation -> ``Easy / Medium / Hard`` AP, ``result.tar.gz``).  The FDDB /
+AFW / PASCAL loaders are out of scope (SURVEY section 2 OUT); they run unmodified through ``compat``.
 """
 from __future__ import annotations
 
@@ -65,12 +66,85 @@ class GeneralImdb:
         return "Detection results wrote to {}".format(output_dir)
 
 
+class WiderImdb:
+    """``lib/datasets/wider.py:21-72,143-195``: WIDER FACE ``train`` / ``val`` / ``test``.  Layout under ``DATA_DIR``:
+    ``WIDER_<split>/images/<event>/<name>.jpg``, ``wider_face_split/wider_face_<split>_bbx_gt.txt`` (``test``:
+    ``wider_face_test_filelist.txt``), ``ground_truth/wider_{face,easy,medium,hard}_val.mat``.  Only what the TEST path reads
+    is kept: the image list (in annotation-file order; the reference's Python 2 ``dict.keys()`` order is arbitrary and only
+    permutes the result files) and the evaluation."""
+
+    num_classes = 2
+
+    def __init__(self, cfg, split: str, overlaps=None):
+        self.name = "wider_" + split
+        self.split = split
+        self.classes = ["bg", "face"]
+        self.cfg = cfg
+        self.overlaps = overlaps                      # None: the GPU IoU kernel (wider_eval.py)
+        self.imgs_path = osp.join(cfg.DATA_DIR, "WIDER_{}".format(split), "images")
+        anno = osp.join(cfg.DATA_DIR, "wider_face_split",
+                        "wider_face_test_filelist.txt" if split == "test" else "wider_face_{}_bbx_gt.txt".format(split))
+        assert osp.isfile(anno), "Annotation file not found {}".format(anno)
+        with open(anno, "r") as f:
+            lines = f.readlines()
+        self.image_paths: List[str] = []
+        self.gt_boxes = {}
+        if split == "test":
+            self.image_paths = [str(p).rstrip() for p in lines]
+        else:
+            count = 0
+            while count < len(lines):                 # wider.py:46-61
+                name = str(lines[count]).rstrip()
+                boxes = []
+                count += 1
+                n_anno = int(lines[count])
+                for _ in range(n_anno):
+                    count += 1
+                    b = [int(round(float(x))) for x in lines[count].split(" ")[0:4]]
+                    x1, y1 = max(0, b[0]), max(0, b[1])
+                    boxes.append([x1, y1, x1 + b[2], y1 + b[3]])
+                count += 1
+                if name not in self.gt_boxes:
+                    self.image_paths.append(name)
+                self.gt_boxes[name] = boxes
+
+    def __len__(self):
+        return len(self.image_paths)
+
+    def image_path_at(self, i):
+        p = osp.join(self.imgs_path, self.image_paths[i])
+        assert osp.exists(p), "Path does not exist: {}".format(p)
+        return p
+
+    def evaluate_detections(self, all_boxes, output_dir="./output/"):
+        """``wider.py:172-195``: text files under ``<output_dir>/detections``, the WIDER toolbox evaluation, ``result.tar.gz``
+        (what the evaluation server takes), the text files removed again.  ``test`` has no public ground truth: the
+        archive is written and nothing is evaluated."""
+        import shutil
+        import tarfile
+        from .wider_eval import format_result, wider_eval
+        det_dir = osp.join(output_dir, "detections")
+        write_detections(self.image_paths, all_boxes[1], det_dir)
+        result = "Detections archived for the evaluation server (no public ground truth for the test split)"
+        if self.split != "test":
+            ap, _ = wider_eval(det_dir, osp.join(self.cfg.DATA_DIR, "ground_truth"), mimic_eval_bug=self.cfg.MISC.MIMIC_EVAL_BUG,
+                               IoU_thresh=self.cfg.TEST.IOU_THRESH, overlaps=self.overlaps)
+            self.ap = ap
+            result = format_result(ap)
+        with tarfile.open(osp.join(output_dir, "result.tar.gz"), "w:gz") as tar:
+            tar.add(det_dir, arcname=osp.basename(det_dir))
+        shutil.rmtree(det_dir)
+        return result
+
+
 def get_imdb(cfg, name: str):
     """``lib/datasets/factory.py:9-34`` for the datasets in scope."""
     if name.startswith("general_") and name[len("general_"):] in ("png", "jpg"):
         return GeneralImdb(cfg.DATA_DIR, name[len("general_"):])
-    if name.split("_")[0] in ("wider", "fddb", "pascalface", "afw"):
-        raise NotImplementedError("dataset %s needs its annotation files; only general_{png,jpg} is in scope here" % name)
+    if name in ("wider_train", "wider_val", "wider_test"):
+        return WiderImdb(cfg, name[len("wider_"):])
+    if name.split("_")[0] in ("fddb", "pascalface", "afw"):
+        raise NotImplementedError("dataset %s: only general_{png,jpg} and wider_{train,val,test} are in scope here" % name)
     raise KeyError("Unknown dataset: {}".format(name))
 
 

@@ -108,6 +108,8 @@ def test_general_imdb_and_output_dir(tree, tmp_path):
     with pytest.raises(KeyError, match="Unknown dataset"):
         R.get_imdb(cfg, "nothing_val")
     with pytest.raises(NotImplementedError):
+        R.get_imdb(cfg, "fddb_val")
+    with pytest.raises(AssertionError, match="Annotation file not found"):        # wider.py:38-39
         R.get_imdb(cfg, "wider_val")
     out = C.get_output_dir(cfg, imdb.name, "face_x", output_dir=str(tmp_path / "o"))
     assert out == str(tmp_path / "o" / "face" / "general_png" / "face_x") and os.path.isdir(out)

@@ -85,3 +85,71 @@ def test_evaluator_on_the_gpu_iou_kernel(tmp_path):
     for bug, thr in ((True, 0.5), (False, 0.3)):
         ap, pr = W.wider_eval(pred_dir, gt_dir, mimic_eval_bug=bug, IoU_thresh=thr)      # default: shf_bbox_overlaps
         _check(ap, pr, "s1_bug%d_t%d" % (int(bug), int(thr * 10)))
+
+
+def _pred_as_all_boxes(pred_dir, imdb):
+    """Detections of the synthetic prediction files as the driver's all_boxes[1] ([x1, y1, x2, y2, score] rows)."""
+    out = []
+    for rel in imdb.image_paths:
+        lines = open(os.path.join(pred_dir, rel[:-4] + ".txt")).read().splitlines()
+        d = np.array([[float(v) for v in ln.split()] for ln in lines[2:2 + int(lines[1])]], dtype=np.float64).reshape(-1, 5)
+        d[:, 2] += d[:, 0]
+        d[:, 3] += d[:, 1]
+        out.append(d)
+    return out
+
+
+def test_wider_imdb_lists_images_and_evaluates_like_the_toolbox(tmp_path):
+    """run_test.WiderImdb (lib/datasets/wider.py): annotation parsing, image paths, evaluate_detections = writer + evaluator
+    + result.tar.gz; the AP equals the evaluator run directly on the same detection files."""
+    import tarfile
+    from smallhardface_b200 import config as C
+    from smallhardface_b200 import run_test as R
+    root = str(tmp_path / "WIDER")
+    pred_dir, gt_dir = wider_synth.make(root, seed=1, with_images=True)
+    cfg = C.load_default(C.write_builtin_tree(str(tmp_path / "tree")))
+    C.cfg_from_list(cfg, ["DATA_DIR", root, "TEST.DB", "wider_val"])
+    imdb = R.get_imdb(cfg, cfg.TEST.DB)
+    imdb.overlaps = OP.bbox_overlaps                     # CPU test: the oracle's IoU instead of the GPU kernel
+    gt = W.load_gt(os.path.join(gt_dir, "wider_face_val.mat"))
+    n_img = sum(gt["file_list"][i][0].shape[0] for i in range(W.EVENT_NUM))
+    assert imdb.name == "wider_val" and len(imdb) == n_img and os.path.isfile(imdb.image_path_at(0))
+    assert imdb.image_paths[0] == "0--Event0/0_Event0_0.jpg"
+    k = next(i for i, p in enumerate(imdb.image_paths) if imdb.gt_boxes[p])
+    ev, nm = imdb.image_paths[k].split("/")
+    e = int(ev.split("--")[0])
+    j = [str(x[0][0]) for x in gt["file_list"][e][0]].index(nm[:-4])
+    g = gt["face_bbx_list"][e][0][j][0][0]
+    assert imdb.gt_boxes[imdb.image_paths[k]][0] == [int(g[0]), int(g[1]), int(g[0] + g[2]), int(g[1] + g[3])]
+    out = tmp_path / "out"
+    out.mkdir()
+    msg = imdb.evaluate_detections([[], _pred_as_all_boxes(pred_dir, imdb)], str(out))
+    ap, _ = W.wider_eval(pred_dir, gt_dir, mimic_eval_bug=True, IoU_thresh=0.5, overlaps=OP.bbox_overlaps)
+    assert msg == W.format_result(ap) and msg.startswith("Easy: 0.0742, Medium: 0.2602, Hard: 0.4050")
+    assert np.array_equal(np.array(imdb.ap), GOLD["s1_bug1_t5_ap"])            # = the reference evaluator's numbers
+    assert not os.path.exists(out / "detections")
+    with tarfile.open(out / "result.tar.gz") as tar:
+        names = tar.getnames()
+    assert "detections/0--Event0/0_Event0_0.txt" in names and sum(n.endswith(".txt") for n in names) == n_img
+
+
+@pytest.mark.gpu
+def test_native_driver_on_a_wider_shaped_tree(tmp_path):
+    """`python -m smallhardface_b200.run_test --amend TEST.DB wider_val ...` end to end on the B200: WIDER directory layout,
+    Detector over every image, result files, the evaluation on the GPU IoU kernel, result.tar.gz."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from smallhardface_b200 import config as C
+    from smallhardface_b200 import deploy
+    from smallhardface_b200 import run_test as R
+    root = str(tmp_path / "WIDER")
+    wider_synth.make(root, seed=0, with_images=True, max_imgs=2)
+    tree = C.write_builtin_tree(str(tmp_path / "tree"))
+    proto, model = deploy.write_synthetic_deployment(str(tmp_path / "deploy"), dilation=True)
+    out_dir, dets, result = R.main(["--root", tree, "--conf", "configs/smallhardface.toml", "--output", str(tmp_path / "out"), "--amend",
+                                    "DATA_DIR", root, "TEST.DB", "wider_val", "TEST.MODEL", model, "TEST.GPU_ID", "[0]",
+                                    "TEST.SCALES", "[100, 300]"])
+    assert result.startswith("Easy: ") and os.path.isfile(os.path.join(out_dir, "result.tar.gz"))
+    assert len(dets[1]) > 61 and sum(len(d) for d in dets[1]) > 0
+    print("native driver on a WIDER-shaped tree (%d images, synthetic weights): %s" % (len(dets[1]), result))

@@ -16,12 +16,17 @@ def _cell(items):
     return a
 
 
-def make(root, seed=0, max_imgs=3):
+def make(root, seed=0, max_imgs=3, with_images=False, image_hw=(48, 64)):
+    """``with_images``: also lay out ``WIDER_val/images/<event>/<name>.jpg`` (small random images) and
+    ``wider_face_split/wider_face_val_bbx_gt.txt`` in the format lib/datasets/wider.py:46-61 parses, i.e. a complete
+    ``DATA_DIR`` for the ``wider_val`` imdb."""
     from scipy import io as sio
     rng = np.random.RandomState(seed)
     gt_dir = os.path.join(root, "ground_truth")
     pred_dir = os.path.join(root, "pred")
     os.makedirs(gt_dir, exist_ok=True)
+    anno_lines = []
+    img_rng = np.random.RandomState(seed + 1000)        # images draw from their own stream: boxes / detections do not depend on with_images
     events, files, faces = [], [], []
     keep = {"easy": [], "medium": [], "hard": []}
     for e in range(EVENTS):
@@ -39,6 +44,14 @@ def make(root, seed=0, max_imgs=3):
             wh = rng.choice([8, 12, 16, 24, 32, 64, 100], (n_face, 2))
             gt = np.hstack([xy, wh]).astype(np.float64).reshape(n_face, 4)
             b_e.append(gt)
+            if with_images:
+                import cv2
+                d = os.path.join(root, "WIDER_val", "images", ev)
+                os.makedirs(d, exist_ok=True)
+                cv2.imwrite(os.path.join(d, name + ".jpg"), img_rng.randint(0, 256, image_hw + (3,)).astype(np.uint8))
+                anno_lines.append("%s/%s.jpg\n%d\n" % (ev, name, n_face))
+                for g in gt:
+                    anno_lines.append("%d %d %d %d 0 0 0 0 0 0 \n" % tuple(g))
             sizes = wh.min(axis=1) if n_face else np.zeros(0)
             for k, lim in (("easy", 60), ("medium", 20), ("hard", 0)):
                 idx = np.nonzero(sizes >= lim)[0] + 1                     # 1-based, (k, 1) like the official files
@@ -72,6 +85,10 @@ def make(root, seed=0, max_imgs=3):
         faces.append(_cell(b_e))
         for k in keep:
             keep[k].append(_cell(k_e[k]))
+    if with_images:
+        os.makedirs(os.path.join(root, "wider_face_split"), exist_ok=True)
+        with open(os.path.join(root, "wider_face_split", "wider_face_val_bbx_gt.txt"), "w") as f:
+            f.write("".join(anno_lines))
     base = {"event_list": _cell(events), "file_list": _cell(files), "face_bbx_list": _cell(faces)}
     sio.savemat(os.path.join(gt_dir, "wider_face_val.mat"), base)
     for k in keep:
