@@ -1,0 +1,259 @@
+// The 7x7 stride-2 first convolution of a ResNet-style backbone on the tensor cores (sm_100a): 3 input channels, pad 3,
+// 64 output channels, + bias + ReLU (BatchNorm / Scale folded in by the caller).  conv_layer.cpp:8-28 /
+// base_conv_layer.cpp:255-279 semantics; the fp32 SIMT twin is conv_first_kernel (resnet_kernels.cu), which stays the
+// path for every other kernel size / stride.
+//
+// Same scheme as conv1_tc.cu, with K = 3*7*7 = 147 taps instead of 27: the taps of an output pixel form one K-major
+// operand row
+//     A[m] = [ x_hi(k = 0..159) | x_lo(k = 0..159) ]      k = c*49 + r*7 + s, zero for k >= 147, x = x_hi + x_lo (fp16)
+// = 640 bytes = five 128-byte-swizzled column blocks of a 128-row tile, and the layer is 30 M128 x N64 x K16 tcgen05 MMAs per
+// 128-pixel tile (16 x 8 OUTPUT pixels):
+//     D  = A[:,   0:160] x W_hi^T   (x_hi * w_hi, 10 k-steps)
+//     D += A[:, 160:320] x W_hi^T   (x_lo * w_hi, 10 k-steps)
+//     D += A[:,   0:160] x W_lo^T   (x_hi * w_lo, 10 k-steps)
+// The 37 x 21 x 3 fp32 input patch of a tile is fetched once per CTA (prefetched across the previous tile's epilogue),
+// split to fp16 hi / lo once and staged in shared memory as (hi | lo << 16) words; two threads share a pixel: each builds
+// half of its operand row and, in the epilogue, converts and stores half of its 64 channels.
+#include "common.cuh"
+#include "epilogue_store.cuh"
+
+namespace {
+
+struct C7Params {
+  const float* in;          // (N, 3, H, W) fp32
+  const __half* wpack;      // [2][64][192] fp16: [0] = w_hi(k), [1] = w_lo(k) of w * 2^e, k padded from 147 to 192 with zeros
+  const float* bias;        // 64 or nullptr
+  __half* out;              // activation tensor (N, HO, WO, 64), plane 0
+  long long plane_elems;
+  int N, H, W, HO, WO, pad, relu, out_fmt;
+  int tiles_x, tiles_y, total_tiles;
+  float out_scale;          // 2^-e
+  unsigned int* guard;
+};
+
+constexpr int kThreads7 = 256;
+constexpr int kTH = 16, kTW = 8;                       // output pixels per tile
+constexpr int kKS = 7, kST = 2;
+constexpr int kPH = (kTH - 1) * kST + kKS;             // 37 input rows per tile
+constexpr int kPW = (kTW - 1) * kST + kKS;             // 21 input columns
+constexpr int kHaloWords = 3 * kPH * kPW;              // 2331
+constexpr int kPer = (kHaloWords + kThreads7 - 1) / kThreads7;   // 10
+constexpr int kTaps = 3 * kKS * kKS;                   // 147
+constexpr int kKSteps = 10;                            // 160 / 16
+constexpr int kABlock = 128 * 128, kBBlock = 64 * 128; // bytes of one 64-half column block of A / of a weight matrix
+
+// shared memory: [A 5 blocks 80 KB][W_hi 3 blocks 24 KB][W_lo 24 KB][staging 8 x 2 KB][barrier, tmem slot][bias][halo]
+constexpr int kOffWhi = 5 * kABlock;
+constexpr int kOffWlo = kOffWhi + 3 * kBBlock;
+constexpr int kOffStage = kOffWlo + 3 * kBBlock;
+constexpr int kOffBar = kOffStage + 8 * 2048;
+constexpr int kOffBias = kOffBar + 16;
+constexpr int kOffHalo = kOffBias + 256;
+constexpr int kSmem7 = kOffHalo + kHaloWords * 4;
+
+// Chunks 10 * PART .. + 9 (8 taps each) of the hi half of an operand row and their lo twins, from the staged patch:
+// every tap's patch offset is a compile-time constant.
+template <int PART>
+SHF_DEVICE void build_row_half(uint8_t* arow, const uint32_t* my_halo, int m) {
+#pragma unroll
+  for (int qq = 0; qq < 10; ++qq) {
+    uint32_t v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = 80 * PART + 8 * qq + e;                 // tap index c * 49 + r * 7 + s
+      v[e] = k < kTaps ? my_halo[((k / 49) * kPH + (k % 49) / 7) * kPW + (k % 7)] : 0u;
+    }
+    uint32_t h4[4], l4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h4[e] = __byte_perm(v[2 * e], v[2 * e + 1], 0x5410);  // the hi halves of two taps
+      l4[e] = __byte_perm(v[2 * e], v[2 * e + 1], 0x7632);  // ... and their lo halves
+    }
+    const int ch_hi = 10 * PART + qq, ch_lo = 20 + ch_hi;   // chunk index inside the 640-byte row
+    *reinterpret_cast<uint4*>(arow + (ch_hi >> 3) * kABlock + (((ch_hi & 7) ^ (m & 7)) << 4)) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    *reinterpret_cast<uint4*>(arow + (ch_lo >> 3) * kABlock + (((ch_lo & 7) ^ (m & 7)) << 4)) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads7, 1) conv7_tc_kernel(const C7Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* stage_s = smem + kOffStage;
+  const uint32_t bar = smem_base + kOffBar;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8);
+  float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
+  uint32_t* halo_s = reinterpret_cast<uint32_t*>(smem + kOffHalo);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int quad = warp & 3, part = warp >> 2;   // warps w and w + 4 share a TMEM lane quadrant = 32 pixels
+  const int m = quad * 32 + lane;                // operand / accumulator row = output pixel (y_local * 8 + x_local)
+
+  // weights -> shared memory, 128-byte-swizzled K-major column blocks (16-byte chunk j of row n at j ^ (n & 7))
+  for (int i = threadIdx.x; i < 2 * 64 * 24; i += kThreads7) {
+    const int which = i / (64 * 24), n = (i / 24) % 64, ch = i % 24;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.wpack) + i);
+    *reinterpret_cast<uint4*>(smem + (which ? kOffWlo : kOffWhi) + (ch >> 3) * kBBlock + n * 128 + (((ch & 7) ^ (n & 7)) << 4)) = v;
+  }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 64);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  constexpr uint32_t idesc = umma_idesc_f16(128, 64);
+  const uint64_t a_desc = umma_desc_sw128(smem_base);
+  const uint64_t whi_desc = umma_desc_sw128(smem_base + kOffWhi);
+  const uint64_t wlo_desc = umma_desc_sw128(smem_base + kOffWlo);
+  const bool issuer = (warp == 0) && elect_one();
+  uint32_t phase = 0;
+  float gmax = 0.f;
+
+  int h_rs[kPer];            // (channel << 16) | (row << 8) | column of this thread's patch positions, -1 = unused slot
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int idx = (int)threadIdx.x + i * kThreads7;
+    const int c = idx / (kPH * kPW), rem = idx % (kPH * kPW), r = rem / kPW, s2 = rem % kPW;
+    h_rs[i] = idx < kHaloWords ? ((c << 16) | (r << 8) | s2) : -1;
+  }
+  float nxt[kPer];
+  int nx0 = 0, ny0 = 0, nimg = 0;
+  auto prefetch = [&](int t) {
+    const unsigned tx = (unsigned)p.tiles_x, ty = (unsigned)p.tiles_y;
+    unsigned q = (unsigned)t;
+    const int x0 = (int)(q % tx) * kTW;
+    q /= tx;
+    const int y0 = (int)(q % ty) * kTH, img = (int)(q / ty);
+    nx0 = x0; ny0 = y0; nimg = img;
+    const int iy0 = y0 * kST - p.pad, ix0 = x0 * kST - p.pad;
+    const float* org = p.in + (size_t)img * 3 * p.H * p.W;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int c = h_rs[i] >> 16, r = (h_rs[i] >> 8) & 255, s2 = h_rs[i] & 255;
+      const int iy = iy0 + r, ix = ix0 + s2;
+      const bool ok = h_rs[i] >= 0 && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+      nxt[i] = ok ? __ldg(org + ((size_t)(c * p.H + iy) * p.W + ix)) : 0.f;      // zero padding = skipped loads
+    }
+  };
+  if ((int)blockIdx.x < p.total_tiles) prefetch(blockIdx.x);
+  const uint32_t* my_halo = halo_s + ((m >> 3) * kST) * kPW + (m & 7) * kST;
+
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    const int x0 = nx0, y0 = ny0, img = nimg;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      __half hi, lo;
+      split_h2(nxt[i], hi, lo);
+      if (h_rs[i] >= 0)
+        halo_s[threadIdx.x + i * kThreads7] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
+    __syncthreads();
+    // ---- this pixel's operand row: this thread builds 16-byte chunks q = 10 * part .. + 9 of the hi half (8 taps each)
+    //      and their twins in the lo half (chunk 20 + q); part is warp-uniform ----
+    if (part == 0) build_row_half<0>(smem + m * 128, my_halo, m);
+    else build_row_half<1>(smem + m * 128, my_halo, m);
+    fence_proxy_async_smem();                      // generic-proxy writes above -> visible to the tensor core
+    __syncthreads();
+    if (issuer) {
+      tc_fence_after();
+      // k-step j = halves [16 j, 16 j + 16) of a row: column block j / 4, 32-byte slice j % 4 (descriptor + 2 per slice)
+      auto ka = [&](int j) { return a_desc + (uint64_t)((j >> 2) * (kABlock >> 4) + (j & 3) * 2); };
+      auto kb = [&](uint64_t d, int j) { return d + (uint64_t)((j >> 2) * (kBBlock >> 4) + (j & 3) * 2); };
+#pragma unroll
+      for (int j = 0; j < kKSteps; ++j) umma_f16(tmem_acc, ka(j), kb(whi_desc, j), idesc, j ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < kKSteps; ++j) umma_f16(tmem_acc, ka(kKSteps + j), kb(whi_desc, j), idesc, 1u);
+#pragma unroll
+      for (int j = 0; j < kKSteps; ++j) umma_f16(tmem_acc, ka(j), kb(wlo_desc, j), idesc, 1u);
+      umma_commit(bar);
+    }
+    if (t + (int)gridDim.x < p.total_tiles) prefetch(t + (int)gridDim.x);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    float v[32];
+    {
+      uint32_t r0[32];
+      tmem_ld_32x32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * 32), r0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = fmaf(__uint_as_float(r0[e]), p.out_scale, bias_s[part * 32 + e]);
+    }
+    tc_fence_before();
+    __syncthreads();                               // accumulator, operand tile and halo may be overwritten by the next tile
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    const int y = y0 + (m >> 3), x = x0 + (m & 7);
+    if (p.guard && y < p.HO && x < p.WO) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) gmax = fmaxf(gmax, fabsf(v[e]));
+    }
+    uint8_t* stg = stage_s + warp * 2048;
+    const int qy = y0 + quad * 4;
+    __half* base = p.out + (((size_t)img * p.HO + qy) * p.WO + x0) * (size_t)64;
+    const uint32_t pitch = (uint32_t)p.WO * 64u;
+    auto dst = [&](int row) -> __half* {
+      const int dy = row >> 3, dx = row & 7;
+      return (qy + dy < p.HO && x0 + dx < p.WO) ? base + ((uint32_t)dy * pitch + (uint32_t)dx * 64u) : nullptr;
+    };
+    store_plane<32>(stg, lane, v, 0, p.out_fmt, part * 32, (size_t)p.plane_elems, dst);
+    store_plane<32>(stg, lane, v, 1, p.out_fmt, part * 32, (size_t)p.plane_elems, dst);
+  }
+  range_guard_commit(p.guard, gmax);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, 64);
+  }
+}
+
+}  // namespace
+
+// C ABI -- see include/shf_b200.h
+extern "C" int shf_conv7_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H,
+                            int W, int cout, int pad, float out_scale, int relu, int out_format, unsigned int* range_guard,
+                            void* stream) {
+  SHF_REQUIRE(cout == 64, "shf_conv7_tc: Cout=%d (64 supported)", cout);
+  SHF_REQUIRE(out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8, "shf_conv7_tc: unknown activation format %d", out_format);
+  SHF_REQUIRE(batch >= 1 && pad >= 0 && pad < kKS && H + 2 * pad >= kKS && W + 2 * pad >= kKS, "shf_conv7_tc: bad geometry");
+  C7Params p;
+  p.in = in_nchw;
+  p.wpack = reinterpret_cast<const __half*>(w_packed);
+  p.bias = bias;
+  p.out = reinterpret_cast<__half*>(out_act);
+  p.N = batch; p.H = H; p.W = W; p.pad = pad; p.relu = relu; p.out_fmt = out_format;
+  p.HO = (H + 2 * pad - kKS) / kST + 1;            // conv_layer.cpp:8-28
+  p.WO = (W + 2 * pad - kKS) / kST + 1;
+  p.plane_elems = (long long)batch * p.HO * p.WO * 64;
+  p.tiles_x = (p.WO + kTW - 1) / kTW;
+  p.tiles_y = (p.HO + kTH - 1) / kTH;
+  p.total_tiles = p.tiles_x * p.tiles_y * batch;
+  p.out_scale = out_scale;
+  p.guard = range_guard;
+  const int smem_bytes = 1024 + kSmem7;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static bool attr[64] = {};                     // function attributes are per device
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (dev >= 0 && dev < 64) attr[dev] = true;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  conv7_tc_kernel<<<grid, kThreads7, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}

@@ -111,6 +111,23 @@ def pack_conv1_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
     return out, k
 
 
+def pack_conv7_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
+    """(64, 3, 7, 7) fp32 -> fp16 [2][64][192] for ``shf_conv7_tc``: [0] = hi(k), [1] = lo(k) of w * 2^e with
+    k = c*49 + r*7 + s, zero-padded from 147 to 192 (three 64-half column blocks); returns (packed, e)."""
+    w = np.asarray(w_oihw, dtype=np.float32)
+    co = w.shape[0]
+    if w.shape[1:] != (3, 7, 7):
+        raise ValueError("conv7 weights must be (Cout, 3, 7, 7)")
+    amax = float(np.abs(w).max())
+    k = 0 if amax == 0 or not np.isfinite(amax) else int(14 - math.ceil(math.log2(amax)))
+    k = max(-14, min(k, 24))
+    hi, lo = split_h2_np(w.reshape(co, 147) * np.float32(2.0 ** k))
+    out = np.zeros((2, co, 192), dtype=np.float16)
+    out[0, :, :147] = hi
+    out[1, :, :147] = lo
+    return out, k
+
+
 FMT_H2, FMT_HF8 = L.FMT_H2, L.FMT_HF8
 
 # Range guard thresholds (see include/shf_b200.h, `range_guard`): max |x| of every activation tensor a launch writes.
@@ -308,6 +325,10 @@ class GpuNet:
                         raise L.ShfError("conv %s: 3-channel convs need 64 outputs, kernel <= 11, stride <= 4, no dilation" % l.name)
                     st["w"] = torch.from_numpy(np.array(w, dtype=F32)).to(dev)
                     st["pad"] = p["ph"]
+                    if (p["kh"], p["sh"]) == (7, 2):           # ResNet conv1: tensor cores (shf_conv7_tc)
+                        packed7, k7 = pack_conv7_weights(w)
+                        st["wtc"] = torch.from_numpy(packed7).to(dev)
+                        st["scale"] = float(2.0 ** (-k7))
                     self.ops.append(("conv_first", l, st))
                 else:
                     if p["sh"] != 1 and not (p["kh"] == 1 and p["ph"] == 0):
@@ -602,8 +623,12 @@ class GpuNet:
             out = self._alloc_out(s["top"], n, ho, wo, s["cout"], fmt)
             if out.c_off != 0 or out.c != out.ctot:
                 raise L.ShfError("conv %s writes into a concat window; not supported for the first convolution" % l.name)
-            L.call("shf_conv_first", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], s["k"],
-                   s["stride"], s["pad"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            if "wtc" in s:
+                L.call("shf_conv7_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], s["pad"],
+                       s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            else:
+                L.call("shf_conv_first", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], s["k"],
+                       s["stride"], s["pad"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
         elif kind == "eltwise":
             xs = [x]
             for b in l.bottoms[1:]:
