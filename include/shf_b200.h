@@ -94,12 +94,15 @@ int shf_maxpool(const void* in_h2, void* out_h2, int batch, int H, int W, int C,
 int shf_conv_first(const float* in_nchw, const float* w_oihw, const float* bias, void* out_act, int batch, int H, int W,
                    int cout, int ksize, int stride, int pad, int relu, int out_format, unsigned int* range_guard, void* stream);
 
-/* The ResNet first convolution -- 7x7, stride 2, 3 -> 64 channels -- on the tensor cores: the 147 taps of an output pixel form
- * one split-fp16 K-major operand row (five 128-byte-swizzled column blocks), 30 tcgen05 MMAs per 128-pixel tile.
- * w_packed [dev]: fp16 [2][64][192] of (w * 2^e): [0] = hi(k), [1] = lo(k), k = c*49 + r*7 + s padded to 192 with zeros;
- * out_scale = 2^-e.  Output ((H + 2 pad - 7) / 2 + 1) x ((W + 2 pad - 7) / 2 + 1).  shf_conv_first is its fp32 SIMT twin. */
-int shf_conv7_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H, int W, int cout,
-                 int pad, float out_scale, int relu, int out_format, unsigned int* range_guard, void* stream);
+/* First convolutions (3 -> 64 channels) on the tensor cores: ksize 7 / stride 2 (ResNet conv1) and ksize 3 / stride 1 (the
+ * VGG16 conv1_1; shf_conv1_tc is its one-thread-per-pixel predecessor and regression twin).  The 3 k^2 taps of an output pixel
+ * form one split-fp16 K-major operand row [hi(Kp) | lo(Kp)], Kp = 3 k^2 rounded up to 16, in 128-byte-swizzled column blocks;
+ * 3 Kp / 16 tcgen05 MMAs per 128-pixel tile; two threads per pixel.  w_packed [dev]: fp16 [2][64][64 * WB] of (w * 2^e):
+ * [0] = hi(k), [1] = lo(k), k = (c*ks + r)*ks + s zero-padded to WB whole 64-half blocks (WB = 3 / 1); out_scale = 2^-e.
+ * Output ((H + 2 pad - ks) / stride + 1) x ((W + 2 pad - ks) / stride + 1).  shf_conv_first is the fp32 SIMT twin. */
+int shf_conv_first_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H, int W,
+                      int cout, int ksize, int stride, int pad, float out_scale, int relu, int out_format,
+                      unsigned int* range_guard, void* stream);
 
 /* Test hook: 8 = the conv kernel on CTA pairs (tcgen05 cta_group::2, the product path and the default), 7 = the same
  * persistent streaming-drain kernel with one CTA per tile (regression twin of the pair protocol; same results). */

@@ -1,27 +1,28 @@
-// The 7x7 stride-2 first convolution of a ResNet-style backbone on the tensor cores (sm_100a): 3 input channels, pad 3,
-// 64 output channels, + bias + ReLU (BatchNorm / Scale folded in by the caller).  conv_layer.cpp:8-28 /
-// base_conv_layer.cpp:255-279 semantics; the fp32 SIMT twin is conv_first_kernel (resnet_kernels.cu), which stays the
-// path for every other kernel size / stride.
+// First convolutions (3 input channels -> 64) on the tensor cores (sm_100a), + bias + ReLU (BatchNorm / Scale folded in by
+// the caller): the ResNet conv1 (7x7, stride 2) and the VGG16 conv1_1 (3x3, stride 1) as two instantiations of one kernel.
+// conv_layer.cpp:8-28 / base_conv_layer.cpp:255-279 semantics; the fp32 SIMT twin is conv_first_kernel (resnet_kernels.cu),
+// which stays the path for every other kernel size / stride.
 //
-// Same scheme as conv1_tc.cu, with K = 3*7*7 = 147 taps instead of 27: the taps of an output pixel form one K-major
-// operand row
-//     A[m] = [ x_hi(k = 0..159) | x_lo(k = 0..159) ]      k = c*49 + r*7 + s, zero for k >= 147, x = x_hi + x_lo (fp16)
-// = 640 bytes = five 128-byte-swizzled column blocks of a 128-row tile, and the layer is 30 M128 x N64 x K16 tcgen05 MMAs per
-// 128-pixel tile (16 x 8 OUTPUT pixels):
-//     D  = A[:,   0:160] x W_hi^T   (x_hi * w_hi, 10 k-steps)
-//     D += A[:, 160:320] x W_hi^T   (x_lo * w_hi, 10 k-steps)
-//     D += A[:,   0:160] x W_lo^T   (x_hi * w_lo, 10 k-steps)
-// The 37 x 21 x 3 fp32 input patch of a tile is fetched once per CTA (prefetched across the previous tile's epilogue),
-// split to fp16 hi / lo once and staged in shared memory as (hi | lo << 16) words; two threads share a pixel: each builds
-// half of its operand row and, in the epilogue, converts and stores half of its 64 channels.
+// The K = 3*KS*KS taps of an output pixel (147 / 27) form one K-major operand row
+//     A[m] = [ x_hi(k = 0..Kp-1) | x_lo(k = 0..Kp-1) ]     k = (c*KS + r)*KS + s, zero for k >= K, Kp = K rounded up to 16
+// (160 / 32 halves per part: five / one 128-byte-swizzled column blocks of a 128-row tile), x = x_hi + x_lo (fp16), and the
+// layer is 3 * Kp/16 (30 / 6) M128 x N64 x K16 tcgen05 MMAs per tile of 16 x 8 OUTPUT pixels:
+//     D  = A[:,  0:Kp ] x W_hi^T   (x_hi * w_hi)
+//     D += A[:, Kp:2Kp] x W_hi^T   (x_lo * w_hi)
+//     D += A[:,  0:Kp ] x W_lo^T   (x_hi * w_lo)
+// The fp32 input patch of a tile is fetched once per CTA (prefetched across the previous tile's epilogue), split to fp16
+// hi / lo once and staged in shared memory as (hi | lo << 16) words; TWO threads share a pixel: each builds half of its
+// operand row and, in the epilogue, converts and stores half of its 64 channels (32 accumulator registers per thread, so
+// three 256-thread CTAs fit an SM for the 3x3 kernel: 24 warps against the 16 of conv1_tc.cu, its one-thread-per-pixel
+// predecessor, which is kept as the regression twin).
 #include "common.cuh"
 #include "epilogue_store.cuh"
 
 namespace {
 
-struct C7Params {
+struct FcParams {
   const float* in;          // (N, 3, H, W) fp32
-  const __half* wpack;      // [2][64][192] fp16: [0] = w_hi(k), [1] = w_lo(k) of w * 2^e, k padded from 147 to 192 with zeros
+  const __half* wpack;      // [2][64][64 * WB] fp16: [0] = w_hi(k), [1] = w_lo(k) of w * 2^e, k zero-padded to whole 64-half blocks
   const float* bias;        // 64 or nullptr
   __half* out;              // activation tensor (N, HO, WO, 64), plane 0
   long long plane_elems;
@@ -31,37 +32,44 @@ struct C7Params {
   unsigned int* guard;
 };
 
-constexpr int kThreads7 = 256;
+constexpr int kThreadsFc = 256;
 constexpr int kTH = 16, kTW = 8;                       // output pixels per tile
-constexpr int kKS = 7, kST = 2;
-constexpr int kPH = (kTH - 1) * kST + kKS;             // 37 input rows per tile
-constexpr int kPW = (kTW - 1) * kST + kKS;             // 21 input columns
-constexpr int kHaloWords = 3 * kPH * kPW;              // 2331
-constexpr int kPer = (kHaloWords + kThreads7 - 1) / kThreads7;   // 10
-constexpr int kTaps = 3 * kKS * kKS;                   // 147
-constexpr int kKSteps = 10;                            // 160 / 16
 constexpr int kABlock = 128 * 128, kBBlock = 64 * 128; // bytes of one 64-half column block of A / of a weight matrix
 
-// shared memory: [A 5 blocks 80 KB][W_hi 3 blocks 24 KB][W_lo 24 KB][staging 8 x 2 KB][barrier, tmem slot][bias][halo]
-constexpr int kOffWhi = 5 * kABlock;
-constexpr int kOffWlo = kOffWhi + 3 * kBBlock;
-constexpr int kOffStage = kOffWlo + 3 * kBBlock;
-constexpr int kOffBar = kOffStage + 8 * 2048;
-constexpr int kOffBias = kOffBar + 16;
-constexpr int kOffHalo = kOffBias + 256;
-constexpr int kSmem7 = kOffHalo + kHaloWords * 4;
+template <int KS, int ST>
+struct Fc {
+  static constexpr int kPH = (kTH - 1) * ST + KS;      // input rows / columns of a tile's patch (37 x 21, 18 x 10)
+  static constexpr int kPW = (kTW - 1) * ST + KS;
+  static constexpr int kHaloWords = 3 * kPH * kPW;
+  static constexpr int kPer = (kHaloWords + kThreadsFc - 1) / kThreadsFc;
+  static constexpr int kTaps = 3 * KS * KS;
+  static constexpr int kKSteps = (kTaps + 15) / 16;    // k-steps (16 halves) per operand part
+  static constexpr int kChunksPart = 2 * kKSteps;      // 16-byte chunks per part (hi or lo) of a row
+  static constexpr int kABlocks = (2 * kChunksPart + 7) / 8;
+  static constexpr int kWBlocks = (kChunksPart + 7) / 8;
+  // shared memory: [A][W_hi][W_lo][staging 8 x 2 KB][barrier, tmem slot][bias][patch]
+  static constexpr int kOffWhi = kABlocks * kABlock;
+  static constexpr int kOffWlo = kOffWhi + kWBlocks * kBBlock;
+  static constexpr int kOffStage = kOffWlo + kWBlocks * kBBlock;
+  static constexpr int kOffBar = kOffStage + 8 * 2048;
+  static constexpr int kOffBias = kOffBar + 16;
+  static constexpr int kOffHalo = kOffBias + 256;
+  static constexpr int kSmem = kOffHalo + kHaloWords * 4;
+};
 
-// Chunks 10 * PART .. + 9 (8 taps each) of the hi half of an operand row and their lo twins, from the staged patch:
-// every tap's patch offset is a compile-time constant.
-template <int PART>
+// Half of the chunks (8 taps each) of the hi part of an operand row and their lo twins, from the staged patch: every tap's
+// patch offset is a compile-time constant.
+template <int KS, int ST, int PART>
 SHF_DEVICE void build_row_half(uint8_t* arow, const uint32_t* my_halo, int m) {
+  using C = Fc<KS, ST>;
+  constexpr int kMine = C::kChunksPart / 2;
 #pragma unroll
-  for (int qq = 0; qq < 10; ++qq) {
+  for (int qq = 0; qq < kMine; ++qq) {
     uint32_t v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = 80 * PART + 8 * qq + e;                 // tap index c * 49 + r * 7 + s
-      v[e] = k < kTaps ? my_halo[((k / 49) * kPH + (k % 49) / 7) * kPW + (k % 7)] : 0u;
+      const int k = 8 * (kMine * PART + qq) + e;            // tap index (c * KS + r) * KS + s
+      v[e] = k < C::kTaps ? my_halo[((k / (KS * KS)) * C::kPH + (k % (KS * KS)) / KS) * C::kPW + (k % KS)] : 0u;
     }
     uint32_t h4[4], l4[4];
 #pragma unroll
@@ -69,13 +77,20 @@ SHF_DEVICE void build_row_half(uint8_t* arow, const uint32_t* my_halo, int m) {
       h4[e] = __byte_perm(v[2 * e], v[2 * e + 1], 0x5410);  // the hi halves of two taps
       l4[e] = __byte_perm(v[2 * e], v[2 * e + 1], 0x7632);  // ... and their lo halves
     }
-    const int ch_hi = 10 * PART + qq, ch_lo = 20 + ch_hi;   // chunk index inside the 640-byte row
+    const int ch_hi = kMine * PART + qq, ch_lo = C::kChunksPart + ch_hi;   // chunk index inside the row
     *reinterpret_cast<uint4*>(arow + (ch_hi >> 3) * kABlock + (((ch_hi & 7) ^ (m & 7)) << 4)) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
     *reinterpret_cast<uint4*>(arow + (ch_lo >> 3) * kABlock + (((ch_lo & 7) ^ (m & 7)) << 4)) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
   }
 }
 
-__global__ void __launch_bounds__(kThreads7, 1) conv7_tc_kernel(const C7Params p) {
+template <int KS, int ST, int MINB>
+__global__ void __launch_bounds__(kThreadsFc, MINB) conv_first_tc_kernel(const FcParams p) {
+  using C = Fc<KS, ST>;
+  constexpr int kPer = C::kPer, kPH = C::kPH, kPW = C::kPW, kHaloWords = C::kHaloWords, kKSteps = C::kKSteps;
+  constexpr int kOffWhi = C::kOffWhi, kOffWlo = C::kOffWlo, kOffStage = C::kOffStage, kOffBar = C::kOffBar;
+  constexpr int kOffBias = C::kOffBias, kOffHalo = C::kOffHalo, kST = ST, kThreads7 = kThreadsFc;
+  constexpr int kWChunks = C::kWBlocks * 8;               // 16-byte chunks per packed weight row
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -90,8 +105,8 @@ __global__ void __launch_bounds__(kThreads7, 1) conv7_tc_kernel(const C7Params p
   const int m = quad * 32 + lane;                // operand / accumulator row = output pixel (y_local * 8 + x_local)
 
   // weights -> shared memory, 128-byte-swizzled K-major column blocks (16-byte chunk j of row n at j ^ (n & 7))
-  for (int i = threadIdx.x; i < 2 * 64 * 24; i += kThreads7) {
-    const int which = i / (64 * 24), n = (i / 24) % 64, ch = i % 24;
+  for (int i = threadIdx.x; i < 2 * 64 * kWChunks; i += kThreads7) {
+    const int which = i / (64 * kWChunks), n = (i / kWChunks) % 64, ch = i % kWChunks;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.wpack) + i);
     *reinterpret_cast<uint4*>(smem + (which ? kOffWlo : kOffWhi) + (ch >> 3) * kBBlock + n * 128 + (((ch & 7) ^ (n & 7)) << 4)) = v;
   }
@@ -158,10 +173,10 @@ __global__ void __launch_bounds__(kThreads7, 1) conv7_tc_kernel(const C7Params p
         halo_s[threadIdx.x + i * kThreads7] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
     }
     __syncthreads();
-    // ---- this pixel's operand row: this thread builds 16-byte chunks q = 10 * part .. + 9 of the hi half (8 taps each)
-    //      and their twins in the lo half (chunk 20 + q); part is warp-uniform ----
-    if (part == 0) build_row_half<0>(smem + m * 128, my_halo, m);
-    else build_row_half<1>(smem + m * 128, my_halo, m);
+    // ---- this pixel's operand row: this thread builds half of the chunks of the hi part (8 taps each) and their twins in
+    //      the lo part; part is warp-uniform ----
+    if (part == 0) build_row_half<KS, ST, 0>(smem + m * 128, my_halo, m);
+    else build_row_half<KS, ST, 1>(smem + m * 128, my_halo, m);
     fence_proxy_async_smem();                      // generic-proxy writes above -> visible to the tensor core
     __syncthreads();
     if (issuer) {
@@ -220,40 +235,51 @@ __global__ void __launch_bounds__(kThreads7, 1) conv7_tc_kernel(const C7Params p
   }
 }
 
+template <int KS, int ST, int MINB>
+int launch_first_tc(FcParams& p, cudaStream_t stream) {
+  using C = Fc<KS, ST>;
+  p.HO = (p.H + 2 * p.pad - KS) / ST + 1;              // conv_layer.cpp:8-28
+  p.WO = (p.W + 2 * p.pad - KS) / ST + 1;
+  p.plane_elems = (long long)p.N * p.HO * p.WO * 64;
+  p.tiles_x = (p.WO + kTW - 1) / kTW;
+  p.tiles_y = (p.HO + kTH - 1) / kTH;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.N;
+  const int smem_bytes = 1024 + C::kSmem;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static bool attr[64] = {};                     // function attributes are per device
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel<KS, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (dev >= 0 && dev < 64) attr[dev] = true;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int cap = sms * MINB;
+  const int grid = p.total_tiles < cap ? p.total_tiles : cap;
+  conv_first_tc_kernel<KS, ST, MINB><<<grid, kThreadsFc, smem_bytes, stream>>>(p);
+  SHF_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 // C ABI -- see include/shf_b200.h
-extern "C" int shf_conv7_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H,
-                            int W, int cout, int pad, float out_scale, int relu, int out_format, unsigned int* range_guard,
-                            void* stream) {
-  SHF_REQUIRE(cout == 64, "shf_conv7_tc: Cout=%d (64 supported)", cout);
-  SHF_REQUIRE(out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8, "shf_conv7_tc: unknown activation format %d", out_format);
-  SHF_REQUIRE(batch >= 1 && pad >= 0 && pad < kKS && H + 2 * pad >= kKS && W + 2 * pad >= kKS, "shf_conv7_tc: bad geometry");
-  C7Params p;
+extern "C" int shf_conv_first_tc(const float* in_nchw, const void* w_packed, const float* bias, void* out_act, int batch, int H,
+                                 int W, int cout, int ksize, int stride, int pad, float out_scale, int relu, int out_format,
+                                 unsigned int* range_guard, void* stream) {
+  SHF_REQUIRE(cout == 64, "shf_conv_first_tc: Cout=%d (64 supported)", cout);
+  SHF_REQUIRE((ksize == 7 && stride == 2) || (ksize == 3 && stride == 1),
+              "shf_conv_first_tc: kernel %d stride %d (7x7/2 and 3x3/1 have tensor-core instantiations; use shf_conv_first)", ksize, stride);
+  SHF_REQUIRE(out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8, "shf_conv_first_tc: unknown activation format %d", out_format);
+  SHF_REQUIRE(batch >= 1 && pad >= 0 && pad < ksize && H + 2 * pad >= ksize && W + 2 * pad >= ksize, "shf_conv_first_tc: bad geometry");
+  FcParams p;
   p.in = in_nchw;
   p.wpack = reinterpret_cast<const __half*>(w_packed);
   p.bias = bias;
   p.out = reinterpret_cast<__half*>(out_act);
   p.N = batch; p.H = H; p.W = W; p.pad = pad; p.relu = relu; p.out_fmt = out_format;
-  p.HO = (H + 2 * pad - kKS) / kST + 1;            // conv_layer.cpp:8-28
-  p.WO = (W + 2 * pad - kKS) / kST + 1;
-  p.plane_elems = (long long)batch * p.HO * p.WO * 64;
-  p.tiles_x = (p.WO + kTW - 1) / kTW;
-  p.tiles_y = (p.HO + kTH - 1) / kTH;
-  p.total_tiles = p.tiles_x * p.tiles_y * batch;
   p.out_scale = out_scale;
   p.guard = range_guard;
-  const int smem_bytes = 1024 + kSmem7;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  static bool attr[64] = {};                     // function attributes are per device
-  if (dev < 0 || dev >= 64 || !attr[dev]) {
-    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    if (dev >= 0 && dev < 64) attr[dev] = true;
-  }
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv7_tc_kernel<<<grid, kThreads7, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  SHF_LAUNCH_CHECK();
-  return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ksize == 7) return launch_first_tc<7, 2, 1>(p, st);
+  return launch_first_tc<3, 1, 3>(p, st);
 }

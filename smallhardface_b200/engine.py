@@ -111,24 +111,31 @@ def pack_conv1_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
     return out, k
 
 
-def pack_conv7_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
-    """(64, 3, 7, 7) fp32 -> fp16 [2][64][192] for ``shf_conv7_tc``: [0] = hi(k), [1] = lo(k) of w * 2^e with
-    k = c*49 + r*7 + s, zero-padded from 147 to 192 (three 64-half column blocks); returns (packed, e)."""
+def pack_conv_first_tc_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
+    """(64, 3, k, k) fp32 -> fp16 [2][64][64 * WB] for ``shf_conv_first_tc``: [0] = hi(t), [1] = lo(t) of w * 2^e with tap
+    index t = (c*k + r)*k + s, zero-padded to WB whole 64-half column blocks (k = 7: 147 -> 192; k = 3: 27 -> 64);
+    returns (packed, e)."""
     w = np.asarray(w_oihw, dtype=np.float32)
-    co = w.shape[0]
-    if w.shape[1:] != (3, 7, 7):
-        raise ValueError("conv7 weights must be (Cout, 3, 7, 7)")
+    co, ci, kh, kw = w.shape
+    if ci != 3 or kh != kw:
+        raise ValueError("first-conv weights must be (Cout, 3, k, k)")
+    taps = 3 * kh * kw
+    ksteps = -(-taps // 16)
+    wb = -(-(2 * ksteps) // 8)
     amax = float(np.abs(w).max())
-    k = 0 if amax == 0 or not np.isfinite(amax) else int(14 - math.ceil(math.log2(amax)))
-    k = max(-14, min(k, 24))
-    hi, lo = split_h2_np(w.reshape(co, 147) * np.float32(2.0 ** k))
-    out = np.zeros((2, co, 192), dtype=np.float16)
-    out[0, :, :147] = hi
-    out[1, :, :147] = lo
-    return out, k
+    e = 0 if amax == 0 or not np.isfinite(amax) else int(14 - math.ceil(math.log2(amax)))
+    e = max(-14, min(e, 24))
+    hi, lo = split_h2_np(w.reshape(co, taps) * np.float32(2.0 ** e))
+    out = np.zeros((2, co, 64 * wb), dtype=np.float16)
+    out[0, :, :taps] = hi
+    out[1, :, :taps] = lo
+    return out, e
 
 
 FMT_H2, FMT_HF8 = L.FMT_H2, L.FMT_HF8
+
+# conv1_1 kernel: "pair" = two threads per pixel (conv_first_tc.cu), "single" = one thread per pixel (conv1_tc.cu)
+_CONV1_IMPL = __import__("os").environ.get("SHF_CONV1_IMPL", "single")
 
 # Range guard thresholds (see include/shf_b200.h, `range_guard`): max |x| of every activation tensor a launch writes.
 F16_MAX = 65504.0          # hi = rn_f16(x) overflows above this in EITHER format: the forward is invalid -> raise
@@ -318,6 +325,9 @@ class GpuNet:
                     packed1, k1 = pack_conv1_weights(w)
                     st["wtc"] = torch.from_numpy(packed1).to(dev)
                     st["scale"] = float(2.0 ** (-k1))
+                    packed2, k2 = pack_conv_first_tc_weights(w)       # two threads per pixel (csrc/conv_first_tc.cu)
+                    st["wtc2"] = torch.from_numpy(packed2).to(dev)
+                    st["scale2"] = float(2.0 ** (-k2))
                     self.ops.append(("conv1", l, st))
                 elif cin == 3:
                     # the first convolution of a ResNet-style backbone (7x7 stride 2 pad 3): fp32 SIMT kernel
@@ -326,7 +336,7 @@ class GpuNet:
                     st["w"] = torch.from_numpy(np.array(w, dtype=F32)).to(dev)
                     st["pad"] = p["ph"]
                     if (p["kh"], p["sh"]) == (7, 2):           # ResNet conv1: tensor cores (shf_conv7_tc)
-                        packed7, k7 = pack_conv7_weights(w)
+                        packed7, k7 = pack_conv_first_tc_weights(w)
                         st["wtc"] = torch.from_numpy(packed7).to(dev)
                         st["scale"] = float(2.0 ** (-k7))
                     self.ops.append(("conv_first", l, st))
@@ -614,8 +624,12 @@ class GpuNet:
         if kind == "conv1":
             n, _, h, w = x.shape
             out = self._alloc_out(s["top"], n, h, w, s["cout"], fmt)
-            L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
-                   s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            if _CONV1_IMPL == "pair":
+                L.call("shf_conv_first_tc", _ptr(x), _ptr(s["wtc2"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], 3, 1, 1,
+                       s["scale2"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            else:
+                L.call("shf_conv1_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"],
+                       s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
         elif kind == "conv_first":
             n, _, h, w = x.shape
             ho = (h + 2 * s["pad"] - s["k"]) // s["stride"] + 1
@@ -624,7 +638,7 @@ class GpuNet:
             if out.c_off != 0 or out.c != out.ctot:
                 raise L.ShfError("conv %s writes into a concat window; not supported for the first convolution" % l.name)
             if "wtc" in s:
-                L.call("shf_conv7_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], s["pad"],
+                L.call("shf_conv_first_tc", _ptr(x), _ptr(s["wtc"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], 7, 2, s["pad"],
                        s["scale"], int(s["relu"]), out.fmt, self._gptr(out.fmt, s["slot"]), st)
             else:
                 L.call("shf_conv_first", _ptr(x), _ptr(s["w"]), _ptr(s["bias"]), _ptr(out.t), n, h, w, s["cout"], s["k"],

@@ -18,7 +18,7 @@ _lib = None
 c_void_p, c_int, c_float, c_double, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
 
 FMT_H2, FMT_HF8 = 0, 1          # SHF_FMT_* of include/shf_b200.h
-ABI_VERSION = 6                 # shf_abi_version() of the library these signatures describe
+ABI_VERSION = 7                 # shf_abi_version() of the library these signatures describe
 
 # name -> (restype, argtypes); must list every symbol include/shf_b200.h declares
 SIGNATURES = {
@@ -41,8 +41,8 @@ SIGNATURES = {
                             c_void_p]),
     "shf_conv_first": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_void_p, c_void_p]),
-    "shf_conv7_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
-                             c_void_p, c_void_p]),
+    "shf_conv_first_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                  c_int, c_int, c_void_p, c_void_p]),
     "shf_set_conv_impl": (c_int, [c_int]),
     "shf_conv1_c3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "shf_conv1_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int,

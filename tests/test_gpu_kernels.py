@@ -94,6 +94,16 @@ def test_conv1_tensor_core_matches_oracle(H, W, fmt):
     simt = H2.empty(2, H, W, 64, DEV, fmt=fmt)
     L.call("shf_conv1_c3", _ptr(dev(x)), _ptr(dev(w)), _ptr(dev(b)), _ptr(simt.t), 2, H, W, 64, 1, fmt, _stream())
     assert relerr(got, simt.to_nchw().cpu().numpy()) < (2e-6 if fmt == 0 else 2 ** -13)
+    # the two-threads-per-pixel instantiation of csrc/conv_first_tc.cu: same operand rows, same MMAs -> the same bits
+    from smallhardface_b200.engine import pack_conv_first_tc_weights
+    packed2, k2 = pack_conv_first_tc_weights(w)
+    assert k2 == k
+    out2 = H2(torch.zeros((2, 2, H, W, 64), dtype=torch.float16, device=DEV), fmt=fmt)
+    L.call("shf_conv_first_tc", _ptr(dev(x)), _ptr(dev(packed2)), _ptr(dev(b)), _ptr(out2.t), 2, H, W, 64, 3, 1, 1, float(2.0 ** -k2), 1,
+           fmt, None, _stream())
+    got2 = out2.to_nchw().cpu().numpy()
+    assert relerr(got2, ref) < (2e-6 if fmt == 0 else 2 ** -14)
+    print("conv1_1 pair kernel vs single-thread kernel: max abs difference %.3g" % float(np.abs(got2 - got).max()))
 
 
 CONV_CASES = [

@@ -146,19 +146,19 @@ def test_conv_first_matches_oracle(H, W, k, s, p, fmt):
 @pytest.mark.parametrize("H,W,pad,fmt,batch", [(64, 96, 3, 0, 2), (37, 53, 3, 1, 2), (9, 9, 3, 0, 1), (224, 224, 3, 1, 1), (40, 31, 0, 0, 3),
                                                (17, 300, 2, 0, 1)])
 def test_conv7_tensor_core_matches_oracle_and_simt_twin(H, W, pad, fmt, batch):
-    """shf_conv7_tc (7x7 stride 2 on tcgen05: 147-tap split-fp16 operand rows, 30 MMAs per tile) vs the oracle and vs its
+    """shf_conv_first_tc, 7x7 stride 2 (on tcgen05: 147-tap split-fp16 operand rows, 30 MMAs per tile) vs the oracle and vs its
     fp32 SIMT twin shf_conv_first."""
-    from smallhardface_b200.engine import pack_conv7_weights
+    from smallhardface_b200.engine import pack_conv_first_tc_weights
     rng = np.random.RandomState(H * 7 + W)
     x = (rng.rand(batch, 3, H, W) * 255 - 110).astype(F32)
     w = (rng.randn(64, 3, 7, 7) * np.sqrt(2.0 / 147)).astype(F32)
     b = (rng.randn(64) * 0.05).astype(F32)
     ref = OL.relu(OL.conv(x, w, b, pad=(pad, pad), stride=(2, 2)))
-    packed, e = pack_conv7_weights(w)
+    packed, e = pack_conv_first_tc_weights(w)
     out = H2(torch.zeros((2, batch, ref.shape[2], ref.shape[3], 64), dtype=torch.float16, device=DEV), fmt=fmt)
     guard = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.call("shf_conv7_tc", _ptr(dev(x)), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), batch, H, W, 64, pad, float(2.0 ** -e), 1, fmt,
-           _ptr(guard), _stream())
+    L.call("shf_conv_first_tc", _ptr(dev(x)), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), batch, H, W, 64, 7, 2, pad, float(2.0 ** -e),
+           1, fmt, _ptr(guard), _stream())
     got = out.to_nchw().cpu().numpy()
     assert got.shape == ref.shape and relerr(got, ref) < (3e-6 if fmt == 0 else 2 ** -14)
     assert abs(float(guard.cpu().numpy().view(F32)[0]) - np.abs(ref).max()) < 1e-3 * np.abs(ref).max()

@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from smallhardface_b200 import lib as L
-from smallhardface_b200.engine import H2, _ptr, _stream, pack_conv1_weights
+from smallhardface_b200.engine import H2, _ptr, _stream, pack_conv1_weights, pack_conv_first_tc_weights
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -28,17 +28,24 @@ try:
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-ts = []
-for it in range(13):
-    flush.fill_(it)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    L.call("shf_conv1_tc", _ptr(x), _ptr(pk), _ptr(bias), _ptr(out.t), B, H, H, 64, float(2.0 ** -k), 1, fmt, None, _stream())
-    e1.record()
-    torch.cuda.synchronize()
-    if it >= 3:
-        ts.append(e0.elapsed_time(e1))
-ms = float(np.median(ts))
+packed2, k2 = pack_conv_first_tc_weights(w)
+pk2 = torch.from_numpy(packed2).to(dev)
 gb = B * H * H * 268 / 1e9
-print("conv1_tc %dx%d batch %d fmt %d: %.3f ms median (min %.3f), %.2f GB algorithmic -> %.0f GB/s = %.3f of %.0f GB/s"
-      % (H, H, B, fmt, ms, min(ts), gb, gb / ms * 1e3, gb / ms * 1e3 / peak, peak))
+for name in ("single (conv1_tc.cu, one thread per pixel)", "pair (conv_first_tc.cu, two threads per pixel)"):
+    ts = []
+    for it in range(13):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if name.startswith("single"):
+            L.call("shf_conv1_tc", _ptr(x), _ptr(pk), _ptr(bias), _ptr(out.t), B, H, H, 64, float(2.0 ** -k), 1, fmt, None, _stream())
+        else:
+            L.call("shf_conv_first_tc", _ptr(x), _ptr(pk2), _ptr(bias), _ptr(out.t), B, H, H, 64, 3, 1, 1, float(2.0 ** -k2), 1, fmt,
+                   None, _stream())
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    print("conv1_1 %s %dx%d batch %d fmt %d: %.3f ms median (min %.3f), %.2f GB algorithmic -> %.0f GB/s = %.3f of %.0f GB/s"
+          % (name, H, H, B, fmt, ms, min(ts), gb, gb / ms * 1e3, gb / ms * 1e3 / peak, peak))
