@@ -335,7 +335,7 @@ class GpuNet:
                         raise L.ShfError("conv %s: 3-channel convs need 64 outputs, kernel <= 11, stride <= 4, no dilation" % l.name)
                     st["w"] = torch.from_numpy(np.array(w, dtype=F32)).to(dev)
                     st["pad"] = p["ph"]
-                    if (p["kh"], p["sh"]) == (7, 2):           # ResNet conv1: tensor cores (shf_conv7_tc)
+                    if (p["kh"], p["sh"]) == (7, 2):           # ResNet conv1: tensor cores (shf_conv_first_tc)
                         packed7, k7 = pack_conv_first_tc_weights(w)
                         st["wtc"] = torch.from_numpy(packed7).to(dev)
                         st["scale"] = float(2.0 ** (-k7))
