@@ -49,3 +49,19 @@ for name in ("single (conv1_tc.cu, one thread per pixel)", "pair (conv_first_tc.
     ms = float(np.median(ts))
     print("conv1_1 %s %dx%d batch %d fmt %d: %.3f ms median (min %.3f), %.2f GB algorithmic -> %.0f GB/s = %.3f of %.0f GB/s"
           % (name, H, H, B, fmt, ms, min(ts), gb, gb / ms * 1e3, gb / ms * 1e3 / peak, peak))
+
+# context: what a pure WRITE stream reaches on this GPU (conv1_1 writes 256 B for every 12 B it reads; the measured peak in
+# MEASURED_PEAKS.json is a copy, i.e. half reads)
+big = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+for label, fn in (("torch fill_ (1 GiB)", lambda: big.fill_(7)), ("cudaMemsetAsync (1 GiB)", lambda: big.zero_())):
+    ts = []
+    for it in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    print("pure write, %s: %.3f ms -> %.0f GB/s = %.3f of the measured copy peak" % (label, ms, big.numel() / ms / 1e6, big.numel() / ms / 1e6 / peak))
