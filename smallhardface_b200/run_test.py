@@ -149,7 +149,7 @@ def get_imdb(cfg, name: str):
 
 
 def inference(cfg, imdb, prototxt_path: str, start: int, end: int, thresh: float = 0.05, batch: int = 8, device="cuda:0",
-              detector=None):
+              detector=None, group_by_size: bool = True):
     """``lib/test.py:220-267`` inference_worker for images [start, end): returns ``all_boxes[class][image]``.
     ``detector``: reuse a built ``Detector`` (weights loaded and packed) instead of constructing one."""
     import cv2
@@ -161,23 +161,40 @@ def inference(cfg, imdb, prototxt_path: str, start: int, end: int, thresh: float
     # GPU; images reach the device as uint8 through page-locked staging (Detector.upload) and are resized there.
     from concurrent.futures import ThreadPoolExecutor
 
-    def load(i0):
-        paths = [imdb.image_path_at(i) for i in range(i0, min(i0 + batch, end))]
+    def load(idxs):
+        paths = [imdb.image_path_at(i) for i in idxs]
         return paths, list(pool.map(cv2.imread, paths))
 
-    starts = list(range(start, end, batch))
     with ThreadPoolExecutor(max_workers=max(1, min(batch, os.cpu_count() or 1))) as pool, \
             ThreadPoolExecutor(max_workers=1) as ahead:
-        nxt = ahead.submit(load, starts[0]) if starts else None
-        for k, i0 in enumerate(starts):
+        # Same-sized images are batched per pyramid level (Detector.detect), so the shard is walked in size order -- image
+        # headers only (PIL parses them without decoding) -- and the results go back to their own slots.  Results do not
+        # depend on the order: every image is processed independently.
+        order = list(range(start, end))
+        if group_by_size and len(order) > batch:
+            try:
+                from PIL import Image
+
+                def size_of(i):
+                    with Image.open(imdb.image_path_at(i)) as im:
+                        return im.size
+                sizes = list(pool.map(size_of, order))
+                order = [i for _, i in sorted(zip(sizes, order), key=lambda t: (t[0], t[1]))]
+            except Exception as e:                                     # unreadable header: keep the list order
+                logger.warning("size scan failed (%s); images are taken in list order", e)
+        chunks = [order[k:k + batch] for k in range(0, len(order), batch)]
+        nxt = ahead.submit(load, chunks[0]) if chunks else None
+        done = 0
+        for k, idxs in enumerate(chunks):
             paths, images = nxt.result()
-            nxt = ahead.submit(load, starts[k + 1]) if k + 1 < len(starts) else None
+            nxt = ahead.submit(load, chunks[k + 1]) if k + 1 < len(chunks) else None
             for p, im in zip(paths, images):
                 if im is None:
                     raise IOError("cv2.imread failed on {}".format(p))
-            for j, d in enumerate(det.detect(images)):
-                all_boxes[1][i0 - start + j] = d
-            logger.info("im_detect: %d/%d", min(i0 + batch, end) - start, end - start)
+            for i, d in zip(idxs, det.detect(images)):
+                all_boxes[1][i - start] = d
+            done += len(idxs)
+            logger.info("im_detect: %d/%d", done, end - start)
     return all_boxes
 
 
