@@ -9,8 +9,11 @@ from oracle import detect as OD, preprocess as PRE
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 proto, model = deploy.write_synthetic_deployment(os.path.join(tempfile.gettempdir(), "shf_b200_deploy"), dilation=True)
 onet = OracleNet(proto, model, engine="torch", fast=True)
-im = deploy.synthetic_image(3)
 levels = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [100, 300]
+kind = sys.argv[2] if len(sys.argv) > 2 else "bench"          # "bench" = the multi-octave image bench.py times, "randint" = white noise
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+im = deploy.synthetic_image(seed) if kind == "bench" else np.random.RandomState(seed).randint(0, 256, (1024, 1024, 3)).astype(np.uint8)
+print("# image: %s seed %d" % (kind, seed), flush=True)
 for lv, fast_min in [(lv, fm) for lv in levels for fm in (None, 0.0)]:
     cfg = DetectConfig(scales=(lv, lv + 1), flip=False, thresh=0.002, fast_min_scale=fast_min)     # two scales -> pyramid mode; use pass 0 only
     det = Detector(proto, model, "cuda:0", cfg)
