@@ -1,6 +1,6 @@
 """One pyramid level of the ResNet-50-through-res3 detection net (models.build_resnet_test_net) on the B200: CUDA-event time
 per launch kind (first conv, tcgen05 convs, residual adds, pooling), both operand formats.
-usage: resnet_level.py [H] [batch]"""
+usage: resnet_level.py [H] [batch] [nofuse]"""
 import os
 import sys
 import tempfile
@@ -17,10 +17,11 @@ from smallhardface_b200.graph import NetSpec, load_weights
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 1408
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+FUSE = not (len(sys.argv) > 3 and sys.argv[3] == "nofuse")      # nofuse: residual adds as Eltwise launches of their own
 proto, model = deploy.write_synthetic_resnet_deployment(os.path.join(tempfile.gettempdir(), "shf_resnet"), blocks=(3, 4), input_hw=(H, H))
 spec = NetSpec(cp.read_net_text(proto))
 shapes = spec.infer_shapes({"data": (B, 3, H, H)})
-gnet = GpuNet(spec, load_weights(spec, cp.read_net_binary(model)), "cuda:0", fast_min_scale=0.9)
+gnet = GpuNet(spec, load_weights(spec, cp.read_net_binary(model)), "cuda:0", fast_min_scale=0.9, fuse_pool=FUSE)
 flops = 0.0
 for l in spec.layers:
     if l.type == "Convolution":
