@@ -121,6 +121,55 @@ def test_general_imdb_and_output_dir(tree, tmp_path):
     assert text[0] == imdb.image_paths[0] and text[1] == "1" and text[2] == "1 2 29 38 0.93 "
 
 
+def test_inference_walks_images_in_size_order_and_returns_them_in_list_order(tree, tmp_path):
+    """run_test.inference: same-sized images are grouped into batches (header scan), decoded on worker threads one batch
+    ahead, and every result lands in the slot of ITS image -- checked with a stand-in detector that reports what it saw."""
+    import cv2
+    from smallhardface_b200 import run_test as R
+    imgs = tmp_path / "imgs"
+    imgs.mkdir()
+    rng = np.random.RandomState(2)
+    shapes = [(40, 64), (64, 40), (40, 64), (48, 48), (64, 40), (40, 64), (48, 48)]
+    for i, (h, w) in enumerate(shapes):
+        cv2.imwrite(str(imgs / ("im%02d.png" % i)), np.full((h, w, 3), 10 + i, np.uint8))
+    cfg = C.load_default(tree)
+    C.cfg_from_list(cfg, ["DATA_DIR", str(imgs), "TEST.DB", "general_png"])
+    imdb = R.get_imdb(cfg, cfg.TEST.DB)
+    want = {p: cv2.imread(p) for p in imdb.image_paths}
+
+    class FakeDetector:
+        batches = []
+
+        def detect(self, images):
+            FakeDetector.batches.append([im.shape[:2] for im in images])
+            return [np.array([[im.shape[0], im.shape[1], float(im[0, 0, 0]), 0, 1.0]]) for im in images]
+
+    for grouped in (True, False):
+        FakeDetector.batches = []
+        boxes = R.inference(cfg, imdb, None, 0, len(imdb), batch=2, detector=FakeDetector(), group_by_size=grouped)
+        assert len(boxes[1]) == len(imdb)
+        for i, p in enumerate(imdb.image_paths):
+            h, w, v = boxes[1][i][0, :3]
+            assert (h, w) == want[p].shape[:2] and v == float(want[p][0, 0, 0]), (grouped, i)
+        mixed = sum(1 for b in FakeDetector.batches if len(set(b)) > 1)
+        assert sum(len(b) for b in FakeDetector.batches) == len(imdb)
+        if grouped:
+            assert mixed <= 2                    # at most the batches that straddle two size groups
+    # a sub-range keeps its own slots
+    part = R.inference(cfg, imdb, None, 2, 5, batch=2, detector=FakeDetector())
+    assert [tuple(b[0, :2]) for b in part[1]] == [want[p].shape[:2] for p in imdb.image_paths[2:5]]
+
+
+def test_cli_refuses_training_and_unknown_keys(tree):
+    from smallhardface_b200 import run_test as R
+    with pytest.raises(SystemExit, match="training is outside"):
+        R.main(["--root", tree, "--train", "true"])
+    with pytest.raises(KeyError):
+        R.build_cfg(tree, "configs/smallhardface.toml", ["TEST.NOT_A_KEY", "1"])
+    cfg = R.build_cfg(tree, "configs/smallhardface.toml", ["TEST.GPU_ID", "[2, 3]"])
+    assert cfg.TEST.NO_CACHE is True and cfg.TEST.GPU_ID == [2, 3] and R._first_gpu(cfg) == 2 and cfg.LOG.TIME
+
+
 @pytest.mark.gpu
 def test_native_driver_equals_detector_and_caches(tmp_path):
     """`python -m smallhardface_b200.run_test` end to end on the B200: config files, deploy prototxt with the dim_red splice,
