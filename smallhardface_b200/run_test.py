@@ -292,6 +292,9 @@ def main(argv=None):
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
+        stamp = [cfg.LOG.TIME]                          # one output directory for the job: rank 0's time stamp
+        dist.broadcast_object_list(stamp, src=0)
+        cfg.LOG.TIME = stamp[0]
     if cfg.TEST.DEMO.ENABLE:
         raise NotImplementedError("TEST.DEMO draws boxes with cv2 on one image; use Detector.detect directly")
     imdb = get_imdb(cfg, cfg.TEST.DB)
