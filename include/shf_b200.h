@@ -74,6 +74,14 @@ int shf_conv_igemm_res(const void* in_h2, const void* w_h2, const float* bias, c
                        int res_channels_total, int res_channel_offset, float out_scale, int relu, int in_format, int res_format,
                        int out_format, unsigned int* range_guard, void* stream);
 
+/* 3x3 convolution with stride 2 and pad 1 (stage transitions of torchvision-style ResNets and similar backbones): H x W are
+ * the INPUT dims (both >= 2), the output is ((H - 1) / 2 + 1) x ((W - 1) / 2 + 1).  w_h2 as for a 3x3 shf_conv_igemm.  The
+ * tcgen05 kernel walks (tap, 64-channel chunk) pairs and reads every tap from the parity view of the input it lives in
+ * (four strided TMA maps; TMA zero fill outside a view is the zero padding): no gather pass, no MMAs on discarded pixels. */
+int shf_conv3x3_s2(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W, int cin,
+                   int cout, int out_channels_total, int out_channel_offset, float out_scale, int relu, int in_format,
+                   int out_format, unsigned int* range_guard, void* stream);
+
 /* ---- layers a ResNet-style backbone adds (BASELINE north_star names "the ResNet/VGG backbone"; csrc/resnet_kernels.cu) -- */
 /* EltwiseLayer SUM (eltwise_layer.cpp:37-77): out = sum_t coeffs[t] * ins[t] over n_in (<= 4) activation tensors of
  * `pixels` x C [dev; ins is a HOST array of device pointers], coeffs [host, may be NULL = all 1], optionally followed by the

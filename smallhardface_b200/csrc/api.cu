@@ -17,7 +17,7 @@ void shf_set_error(const char* fmt, ...) {
 
 extern "C" const char* shf_last_error(void) { return g_err; }
 
-extern "C" int shf_abi_version(void) { return 7; }
+extern "C" int shf_abi_version(void) { return 8; }
 
 extern "C" int shf_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, long long* total_mem) {
   cudaDeviceProp prop;

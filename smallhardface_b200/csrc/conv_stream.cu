@@ -68,6 +68,14 @@ struct StreamParams {
   const __half* res;          // nullptr: none
   long long res_plane_elems;
   int res_ctot, res_coffset, res_fmt;
+  // 3x3 stride-2 mode (template S3): cin_chunks counts (tap, 64-channel chunk) pairs, cin_real the chunks per tap
+  int cin_real;
+};
+
+// Activation tensor maps of a launch.  Every mode but S3 uses m[0]; the 3x3 stride-2 mode reads the input through its four
+// parity views (rows / columns of one parity each: pixel and row pitch doubled, base shifted by one row / pixel).
+struct TmapA4 {
+  CUtensorMap m[4];
 };
 
 SHF_DEVICE void mbar_arrive_cnt(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -83,9 +91,13 @@ constexpr bool kProbes = false;               // product builds: the timing prob
 // instructions and 550 cycles per 8-MMA weight stage, pacing every layer -- the N = 64 ones at half the tensor rate).
 // RES = the launch adds a residual tensor in its epilogue (ResNet blocks): an instantiation of its own, so that the staged
 // row loads do not cost the VGG path registers (the 128-wide variants sit at the 168-register cap).
-template <int BN, int CTAS, int FMT, bool RES = false>
+// S3 = 3x3 convolution with stride 2 (pad 1): output pixel (y, x) reads input (2y + r - 1, 2x + s - 1).  Tap (r, s) lives in
+// the parity view ((r + 1) & 1, (s + 1) & 1) of the input at view coordinates (y - [r == 0], x - [s == 0]), so the layer
+// runs as a 1x1-style K loop over 9 * Cin / 64 (tap, chunk) pairs, each with ONE un-haloed TMA load from its tap's view
+// (TMA zero fill outside a view = the zero padding) and the tap's weight stage -- no gather pass, no wasted MMAs.
+template <int BN, int CTAS, int FMT, bool RES = false, bool S3 = false>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+conv_stream_kernel(const __grid_constant__ TmapA4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                    const StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -114,7 +126,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   constexpr uint32_t kSetCols = 2 * BN;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmaps_a.m[0]);
+    if (S3) { tma_prefetch_desc(&tmaps_a.m[1]); tma_prefetch_desc(&tmaps_a.m[2]); tma_prefetch_desc(&tmaps_a.m[3]); }
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kMaxA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < kMaxB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
@@ -154,16 +167,18 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (p.b_resident && !first) break;     // weights stay in shared memory for every tile of this CTA
         first = false;
         for (int cc = 0; cc < p.cin_chunks; ++cc)
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tap0 = 0; tap0 < p.taps; ++tap0) {
+            // S3: the K loop walks (tap, chunk) pairs; the weight stage of pair cc is chunk cc % cin_real of tap cc / cin_real
+            const int tap = S3 ? cc / p.cin_real : tap0, wc = S3 ? cc % p.cin_real : cc;
             mbar_wait(empty_b(sb), phb ^ 1);
             if (CTAS == 2) {
               // both CTAs credit the LEADER's barrier; each loads its half of the output channels (hi and lo plane)
               if (rank == 0) mbar_arrive_expect_tx(full_b(sb), 2 * p.b_bytes);
-              tma_load_4d_pair(b_stage(sb), &tmap_b, mapa_shared(full_b(sb), 0), cc * kChunkK,
+              tma_load_4d_pair(b_stage(sb), &tmap_b, mapa_shared(full_b(sb), 0), wc * kChunkK,
                                nt * BN + (int)rank * (BN / 2), tap, 0);
             } else {
               mbar_arrive_expect_tx(full_b(sb), p.b_bytes);
-              tma_load_4d(b_stage(sb), &tmap_b, full_b(sb), cc * kChunkK, nt * BN, tap, 0);
+              tma_load_4d(b_stage(sb), &tmap_b, full_b(sb), wc * kChunkK, nt * BN, tap, 0);
             }
             if (++sb == p.nb) { sb = 0; phb ^= 1; }
           }
@@ -186,12 +201,19 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(empty_a(sa), pha ^ 1);
           if (kProbes && (p.probe & 4)) {       // timing probe: no activation loads at all
             if (rank == 0) mbar_arrive(full_a(sa));
-          } else if (CTAS == 2) {
-            if (rank == 0) mbar_arrive_expect_tx(full_a(sa), 2 * p.a_tx);
-            tma_load_5d_pair(a_stage(sa), &tmap_a, mapa_shared(full_a(sa), 0), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
           } else {
-            mbar_arrive_expect_tx(full_a(sa), p.a_tx);
-            tma_load_5d(a_stage(sa), &tmap_a, full_a(sa), cc * kChunkK, x0 - p.pad, y0 - p.pad, img, 0);
+            // S3: tap (r, s) of pair cc -> parity view and view-coordinate shift (see the template comment)
+            const int tap = S3 ? cc / p.cin_real : 0, ac = S3 ? cc % p.cin_real : cc;
+            const int r = tap / 3, s3 = tap - 3 * r;
+            const CUtensorMap* ma = S3 ? &tmaps_a.m[(((r + 1) & 1) << 1) | ((s3 + 1) & 1)] : &tmaps_a.m[0];
+            const int ax = S3 ? x0 - (s3 == 0 ? 1 : 0) : x0 - p.pad, ay = S3 ? y0 - (r == 0 ? 1 : 0) : y0 - p.pad;
+            if (CTAS == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(full_a(sa), 2 * p.a_tx);
+              tma_load_5d_pair(a_stage(sa), ma, mapa_shared(full_a(sa), 0), ac * kChunkK, ax, ay, img, 0);
+            } else {
+              mbar_arrive_expect_tx(full_a(sa), p.a_tx);
+              tma_load_5d(a_stage(sa), ma, full_a(sa), ac * kChunkK, ax, ay, img, 0);
+            }
           }
           if (++sa == p.na) { sa = 0; pha ^= 1; }
         }
@@ -523,18 +545,18 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
-template <int BN, int CTAS, int FMT, bool RES = false>
-int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
+template <int BN, int CTAS, int FMT, bool RES = false, bool S3 = false>
+int launch_stream(const TmapA4& ta, const CUtensorMap& tb, const StreamParams& p, int smem_bytes, int grid,
                   cudaStream_t stream) {
   static bool attr[64] = {};                   // function attributes are per device
   int dev = 0;
   SHF_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr[dev]) {
-    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS, FMT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SHF_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<BN, CTAS, FMT, RES, S3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   if (CTAS == 1) {
-    conv_stream_kernel<BN, CTAS, FMT, RES><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    conv_stream_kernel<BN, CTAS, FMT, RES, S3><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -548,7 +570,7 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const StreamPara
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS, FMT, RES>, ta, tb, p));
+    SHF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_stream_kernel<BN, CTAS, FMT, RES, S3>, ta, tb, p));
   }
   SHF_LAUNCH_CHECK();
   return 0;
@@ -574,12 +596,16 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
                          float out_scale, int relu, void* pool_out_h2, int pool_channels_total, int pool_channel_offset,
                          int ctas, int in_format, int out_format, unsigned int* range_guard, void* stream,
                          int in_stride = 1, int in_H = 0, int in_W = 0, const void* residual = nullptr,
-                         int res_channels_total = 0, int res_channel_offset = 0, int res_format = 0) {
+                         int res_channels_total = 0, int res_channel_offset = 0, int res_format = 0, int s3 = 0) {
   // in_stride > 1 (1x1 kernels only): H x W are the OUTPUT dims, the activations are read through a strided TMA view
   // of the in_H x in_W input (every in_stride-th pixel) -- conv_layer.cpp:8-28 with kernel 1, pad 0
   SHF_REQUIRE(ctas == 1 || ctas == 2, "shf_conv_igemm: %d CTAs per tile group", ctas);
-  SHF_REQUIRE(in_stride >= 1 && (in_stride == 1 || (ksize == 1 && pool_out_h2 == nullptr)),
-              "shf_conv_igemm: stride %d needs a 1x1 kernel without fused pooling", in_stride);
+  // s3: 3x3 kernel, stride 2, pad 1 (H x W = OUTPUT dims, in_H x in_W the input): runs as a 1x1-style K loop over (tap, chunk)
+  // pairs on the four parity views of the input (template S3 of the kernel)
+  SHF_REQUIRE(in_stride >= 1 && (in_stride == 1 || ((ksize == 1 || s3) && pool_out_h2 == nullptr)),
+              "shf_conv_igemm: stride %d needs a 1x1 kernel (or the 3x3 stride-2 mode) without fused pooling", in_stride);
+  SHF_REQUIRE(!s3 || (ksize == 3 && in_stride == 2 && dilation == 1 && ctas == 2 && residual == nullptr),
+              "shf_conv3x3_s2: needs a 3x3 kernel, stride 2, no dilation, the CTA-pair kernel, no residual");
   SHF_REQUIRE((in_format == SHF_FMT_H2 || in_format == SHF_FMT_HF8) && (out_format == SHF_FMT_H2 || out_format == SHF_FMT_HF8),
               "shf_conv_igemm: unknown activation format %d / %d", in_format, out_format);
   if (out_format == SHF_FMT_HF8)
@@ -624,9 +650,10 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   }
   StreamParams p;
   p.H = H; p.W = W; p.batch = batch;
-  p.cin_chunks = cin / 64;
-  p.taps = ksize * ksize;
-  p.dil = (ksize == 3) ? dilation : 0;
+  p.cin_real = cin / 64;
+  p.cin_chunks = s3 ? 9 * (cin / 64) : cin / 64;
+  p.taps = s3 ? 1 : ksize * ksize;
+  p.dil = (ksize == 3 && !s3) ? dilation : 0;
   p.pad = p.dil;
   p.xw = kTW + 2 * p.pad;
   p.xh = kTH + 2 * p.pad;
@@ -643,7 +670,7 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   if (p.nb > kMaxB) p.nb = kMaxB;
   // conv1_2-class layers (one N tile, 9 stages of weights in all): keep the weights in shared memory for the whole
   // kernel -- streaming them again for every 128-pixel tile was most of that layer's L2->SM traffic
-  p.b_resident = (cout == bn && p.taps * p.cin_chunks <= p.nb && p.na >= 2 && !shf_probe_env("SHF_PROBE_NO_RESIDENT")) ? 1 : 0;
+  p.b_resident = (!s3 && cout == bn && p.taps * p.cin_chunks <= p.nb && p.na >= 2 && !shf_probe_env("SHF_PROBE_NO_RESIDENT")) ? 1 : 0;
   if (p.b_resident) p.nb = p.taps * p.cin_chunks;
   if (const char* e = shf_probe_env("SHF_PROBE_NB")) { int v = atoi(e); if (v >= 2 && v < p.nb) p.nb = v; }
   // (a resident weight tensor may be a single stage: the 64 -> 64 1x1 convolutions of a ResNet bottleneck)
@@ -688,20 +715,35 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   p.res_fmt = res_format;
   const int smem_bytes = p.na * p.a_bytes + p.nb * p.b_bytes + 1024 + 1536 + 8 * 4096;
 
-  CUtensorMap ta, tb;
+  TmapA4 ta4;
+  CUtensorMap tb;
+  CUtensorMap& ta = ta4.m[0];
   {
     uint64_t d[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)batch, 2};
     uint32_t b[5] = {64, (uint32_t)p.xw, (uint32_t)p.xh, 1, 2};
-    if (in_stride == 1) {
+    if (s3) {
+      const uint64_t px = (uint64_t)cin * 2, row = px * (uint64_t)in_W, img = row * (uint64_t)in_H;
+      const uint64_t bs[4] = {px * 2, row * 2, img, img * (uint64_t)batch};
+      for (int py = 0; py < 2; ++py)
+        for (int pxl = 0; pxl < 2; ++pxl) {
+          // rows py, py + 2, ... and columns pxl, pxl + 2, ... of the input; an empty view (1-pixel input) keeps one
+          // zero-filled... cannot be encoded with a zero dim, so H, W >= 2 is required below
+          uint64_t dv[5] = {(uint64_t)cin, (uint64_t)((in_W - pxl + 1) / 2), (uint64_t)((in_H - py + 1) / 2), (uint64_t)batch, 2};
+          uint8_t* basev = reinterpret_cast<uint8_t*>(const_cast<void*>(in_h2)) + (uint64_t)py * row + (uint64_t)pxl * px;
+          if (int e = shf_encode_f16_map(&ta4.m[py * 2 + pxl], basev, 5, dv, b, "parity view", bs)) return e;
+        }
+    } else if (in_stride == 1) {
       if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "activations")) return e;
+      ta4.m[1] = ta4.m[2] = ta4.m[3] = ta;
     } else {
       const uint64_t px = (uint64_t)cin * 2, row = px * (uint64_t)in_W, img = row * (uint64_t)in_H;
       const uint64_t bs[4] = {px * (uint64_t)in_stride, row * (uint64_t)in_stride, img, img * (uint64_t)batch};
       if (int e = shf_encode_f16_map(&ta, const_cast<void*>(in_h2), 5, d, b, "strided activations", bs)) return e;
+      ta4.m[1] = ta4.m[2] = ta4.m[3] = ta;
     }
   }
   {
-    uint64_t d[4] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)p.taps, 2};
+    uint64_t d[4] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)(s3 ? 9 : p.taps), 2};
     uint32_t b[4] = {64, (uint32_t)(bn / ctas), 1, 2};
     if (int e = shf_encode_f16_map(&tb, const_cast<void*>(w_h2), 4, d, b, "weights")) return e;
   }
@@ -709,23 +751,29 @@ static int shf_conv_stream_impl(const void* in_h2, const void* w_h2, const float
   const int grid = (p.total_tiles < groups ? p.total_tiles : groups) * ctas;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool f8 = in_format == SHF_FMT_HF8;
+  if (s3) {
+    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8, false, true>(ta4, tb, p, smem_bytes, grid, st)
+                             : launch_stream<128, 2, SHF_FMT_H2, false, true>(ta4, tb, p, smem_bytes, grid, st);
+    return f8 ? launch_stream<64, 2, SHF_FMT_HF8, false, true>(ta4, tb, p, smem_bytes, grid, st)
+              : launch_stream<64, 2, SHF_FMT_H2, false, true>(ta4, tb, p, smem_bytes, grid, st);
+  }
   if (p.res != nullptr) {
     SHF_REQUIRE(ctas == 2, "shf_conv_igemm_res: the residual epilogue exists for the CTA-pair kernel only");
-    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8, true>(ta, tb, p, smem_bytes, grid, st)
-                             : launch_stream<128, 2, SHF_FMT_H2, true>(ta, tb, p, smem_bytes, grid, st);
-    return f8 ? launch_stream<64, 2, SHF_FMT_HF8, true>(ta, tb, p, smem_bytes, grid, st)
-              : launch_stream<64, 2, SHF_FMT_H2, true>(ta, tb, p, smem_bytes, grid, st);
+    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8, true>(ta4, tb, p, smem_bytes, grid, st)
+                             : launch_stream<128, 2, SHF_FMT_H2, true>(ta4, tb, p, smem_bytes, grid, st);
+    return f8 ? launch_stream<64, 2, SHF_FMT_HF8, true>(ta4, tb, p, smem_bytes, grid, st)
+              : launch_stream<64, 2, SHF_FMT_H2, true>(ta4, tb, p, smem_bytes, grid, st);
   }
   if (ctas == 2) {
-    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
-                             : launch_stream<128, 2, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
-    return f8 ? launch_stream<64, 2, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
-              : launch_stream<64, 2, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
+    if (bn == 128) return f8 ? launch_stream<128, 2, SHF_FMT_HF8>(ta4, tb, p, smem_bytes, grid, st)
+                             : launch_stream<128, 2, SHF_FMT_H2>(ta4, tb, p, smem_bytes, grid, st);
+    return f8 ? launch_stream<64, 2, SHF_FMT_HF8>(ta4, tb, p, smem_bytes, grid, st)
+              : launch_stream<64, 2, SHF_FMT_H2>(ta4, tb, p, smem_bytes, grid, st);
   }
-  if (bn == 128) return f8 ? launch_stream<128, 1, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
-                           : launch_stream<128, 1, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
-  return f8 ? launch_stream<64, 1, SHF_FMT_HF8>(ta, tb, p, smem_bytes, grid, st)
-            : launch_stream<64, 1, SHF_FMT_H2>(ta, tb, p, smem_bytes, grid, st);
+  if (bn == 128) return f8 ? launch_stream<128, 1, SHF_FMT_HF8>(ta4, tb, p, smem_bytes, grid, st)
+                           : launch_stream<128, 1, SHF_FMT_H2>(ta4, tb, p, smem_bytes, grid, st);
+  return f8 ? launch_stream<64, 1, SHF_FMT_HF8>(ta4, tb, p, smem_bytes, grid, st)
+            : launch_stream<64, 1, SHF_FMT_H2>(ta4, tb, p, smem_bytes, grid, st);
 }
 
 // ---- C ABI (include/shf_b200.h) ---------------------------------------------------------------------------------
@@ -785,4 +833,18 @@ extern "C" int shf_conv_igemm_res(const void* in_h2, const void* w_h2, const flo
   return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, H, W, cin, cout, ksize, dilation, out_channels_total,
                               out_channel_offset, out_scale, relu, nullptr, 0, 0, g_conv_ctas, in_format, out_format,
                               range_guard, stream, 1, 0, 0, residual, res_channels_total, res_channel_offset, res_format);
+}
+
+// 3x3 convolution with stride 2 and pad 1 (stage transitions of torchvision-style ResNets and similar backbones): H x W are
+// the INPUT dims (both >= 2), the output is ((H - 1) / 2 + 1) x ((W - 1) / 2 + 1) (conv_layer.cpp:8-28).  w_h2: the 3x3 packing
+// of shf_conv_igemm.  The tcgen05 kernel walks (tap, 64-channel chunk) pairs and reads each tap from the parity view of the
+// input it lives in (strided TMA maps): no gather pass, no MMAs on pixels that are thrown away.
+extern "C" int shf_conv3x3_s2(const void* in_h2, const void* w_h2, const float* bias, void* out_h2, int batch, int H, int W,
+                              int cin, int cout, int out_channels_total, int out_channel_offset, float out_scale, int relu,
+                              int in_format, int out_format, unsigned int* range_guard, void* stream) {
+  SHF_REQUIRE(H >= 2 && W >= 2, "shf_conv3x3_s2: input %dx%d (at least 2 x 2)", H, W);
+  const int HO = (H - 1) / 2 + 1, WO = (W - 1) / 2 + 1;
+  return shf_conv_stream_impl(in_h2, w_h2, bias, out_h2, batch, HO, WO, cin, cout, 3, 1, out_channels_total,
+                              out_channel_offset, out_scale, relu, nullptr, 0, 0, 2, in_format, out_format, range_guard,
+                              stream, 2, H, W, nullptr, 0, 0, 0, 1);
 }

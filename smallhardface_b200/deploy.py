@@ -148,15 +148,16 @@ def write_synthetic_deployment(out_dir: str, dilation: bool = True, seed: int = 
     return proto, model
 
 
-def write_synthetic_resnet_deployment(out_dir: str, blocks=(3, 4), seed: int = RNG_SEED, input_hw=(224, 224)):
+def write_synthetic_resnet_deployment(out_dir: str, blocks=(3, 4), seed: int = RNG_SEED, input_hw=(224, 224),
+                                      stride_on_3x3: bool = False):
     """``models.build_resnet_test_net`` + synthetic weights (He-normal convs, plausible BatchNorm statistics, Scale gains)
     as ``test_resnet.prototxt`` / ``.caffemodel``; returns the two paths."""
     from .models import build_resnet_test_net
     os.makedirs(out_dir, exist_ok=True)
-    tag = "resnet_" + "_".join(str(b) for b in blocks)
+    tag = "resnet_" + "_".join(str(b) for b in blocks) + ("_s3x3" if stride_on_3x3 else "")
     proto = os.path.join(out_dir, "test_%s.prototxt" % tag)
     model = os.path.join(out_dir, "synthetic_%s_seed%d.caffemodel" % (tag, seed))
-    net = build_resnet_test_net(blocks, input_hw)
+    net = build_resnet_test_net(blocks, input_hw, stride_on_3x3=stride_on_3x3)
     tmp = ".tmp%d" % os.getpid()
     if not os.path.exists(proto):
         with open(proto + tmp, "w") as f:

@@ -341,9 +341,10 @@ class GpuNet:
                         st["scale"] = float(2.0 ** (-k7))
                     self.ops.append(("conv_first", l, st))
                 else:
-                    if p["sh"] != 1 and not (p["kh"] == 1 and p["ph"] == 0):
-                        raise L.ShfError("conv %s: a spatial stride is supported on 1x1 convolutions only (the ResNet "
-                                         "projection / downsampling form)" % l.name)
+                    if p["sh"] != 1 and not ((p["kh"] == 1 and p["ph"] == 0) or
+                                             (p["kh"], p["sh"], p["ph"], p["dh"]) == (3, 2, 1, 1)):
+                        raise L.ShfError("conv %s: a spatial stride is supported on 1x1 convolutions (pad 0) and on 3x3 "
+                                         "convolutions with stride 2, pad 1" % l.name)
                     if p["kh"] not in (1, 3) or (p["kh"] == 3 and p["ph"] != p["dh"]) or (p["kh"] == 1 and p["ph"] != 0):
                         raise L.ShfError("conv %s: need 3x3 with pad == dilation or 1x1 with pad 0" % l.name)
                     if cin % 64 or p["num_output"] % 64:
@@ -662,8 +663,12 @@ class GpuNet:
             sd = s["stride"]
             out = self._alloc_out(s["top"], x.n, (x.h - 1) // sd + 1, (x.w - 1) // sd + 1, s["cout"], fmt)
             wts = s["w8"] if x.fmt == FMT_HF8 else s["w"]
-            L.call("shf_conv_igemm_strided", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, sd, s["cin"],
-                   s["cout"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            if s["k"] == 3:
+                L.call("shf_conv3x3_s2", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, s["cin"], s["cout"],
+                       out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
+            else:
+                L.call("shf_conv_igemm_strided", _ptr(x.t), _ptr(wts), _ptr(s["bias"]), _ptr(out.t), x.n, x.h, x.w, sd, s["cin"],
+                       s["cout"], out.ctot, out.c_off, s["scale"], int(s["relu"]), x.fmt, out.fmt, self._gptr(out.fmt, s["slot"]), st)
         elif kind == "conv" and "residual" in s:
             if x.c_off != 0 or x.c != x.ctot:
                 raise L.ShfError("conv %s reads a channel window; not supported" % l.name)

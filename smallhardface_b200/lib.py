@@ -18,7 +18,7 @@ _lib = None
 c_void_p, c_int, c_float, c_double, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
 
 FMT_H2, FMT_HF8 = 0, 1          # SHF_FMT_* of include/shf_b200.h
-ABI_VERSION = 7                 # shf_abi_version() of the library these signatures describe
+ABI_VERSION = 8                 # shf_abi_version() of the library these signatures describe
 
 # name -> (restype, argtypes); must list every symbol include/shf_b200.h declares
 SIGNATURES = {
@@ -34,6 +34,8 @@ SIGNATURES = {
                                        c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p]),
     "shf_conv_igemm_res": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "shf_conv3x3_s2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                               c_int, c_int, c_int, c_void_p, c_void_p]),
     "shf_eltwise_sum": (c_int, [C.POINTER(c_void_p), C.POINTER(c_float), c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p]),
     "shf_pool_out_size": (c_int, [c_int, c_int, c_int, c_int, c_int]),

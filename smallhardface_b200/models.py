@@ -196,7 +196,8 @@ def _res_conv(name, bottom, num_output, kernel, pad, stride) -> Msg:
     return Msg("LayerParameter", name=name, type="Convolution", bottom=[bottom], top=[name], convolution_param=c)
 
 
-def _bottleneck(stage: int, block: str, bottom: str, mid: int, out: int, stride: int, project: bool) -> List[Msg]:
+def _bottleneck(stage: int, block: str, bottom: str, mid: int, out: int, stride: int, project: bool,
+                stride_on_3x3: bool = False) -> List[Msg]:
     pre = "res%d%s" % (stage, block)
     tag = "%d%s" % (stage, block)
     layers: List[Msg] = []
@@ -204,9 +205,10 @@ def _bottleneck(stage: int, block: str, bottom: str, mid: int, out: int, stride:
     if project:
         layers += [_res_conv(pre + "_branch1", bottom, out, 1, 0, stride)] + _bn_scale(tag + "_branch1", pre + "_branch1")
         shortcut = pre + "_branch1"
-    layers += [_res_conv(pre + "_branch2a", bottom, mid, 1, 0, stride)] + _bn_scale(tag + "_branch2a", pre + "_branch2a")
+    s_a, s_b = (1, stride) if stride_on_3x3 else (stride, 1)      # "v1.5" / torchvision put the stride on the 3x3 convolution
+    layers += [_res_conv(pre + "_branch2a", bottom, mid, 1, 0, s_a)] + _bn_scale(tag + "_branch2a", pre + "_branch2a")
     layers.append(relu_layer(pre + "_branch2a_relu", pre + "_branch2a"))
-    layers += [_res_conv(pre + "_branch2b", pre + "_branch2a", mid, 3, 1, 1)] + _bn_scale(tag + "_branch2b", pre + "_branch2b")
+    layers += [_res_conv(pre + "_branch2b", pre + "_branch2a", mid, 3, 1, s_b)] + _bn_scale(tag + "_branch2b", pre + "_branch2b")
     layers.append(relu_layer(pre + "_branch2b_relu", pre + "_branch2b"))
     layers += [_res_conv(pre + "_branch2c", pre + "_branch2b", out, 1, 0, 1)] + _bn_scale(tag + "_branch2c", pre + "_branch2c")
     layers.append(Msg("LayerParameter", name=pre, type="Eltwise", bottom=[shortcut, pre + "_branch2c"], top=[pre]))
@@ -214,8 +216,9 @@ def _bottleneck(stage: int, block: str, bottom: str, mid: int, out: int, stride:
     return layers
 
 
-def build_resnet_test_net(blocks=(3, 4), input_hw=(224, 224)) -> Msg:
-    """ResNet-50 through res3 (``blocks`` = bottlenecks per stage) + the standard detection head."""
+def build_resnet_test_net(blocks=(3, 4), input_hw=(224, 224), stride_on_3x3: bool = False) -> Msg:
+    """ResNet-50 through res3 (``blocks`` = bottlenecks per stage) + the standard detection head.  ``stride_on_3x3``: the
+    stage transition strides the 3x3 convolution (torchvision / "v1.5") instead of the first 1x1 (the original Caffe model)."""
     net = Msg("NetParameter", name="face_resnet")
     net.input = ["data", "im_info"]
     net.input_shape = [Msg("BlobShape", dim=[1, 3, int(input_hw[0]), int(input_hw[1])]), Msg("BlobShape", dim=[1, 3])]
@@ -228,7 +231,8 @@ def build_resnet_test_net(blocks=(3, 4), input_hw=(224, 224)) -> Msg:
         mid, out = 64 << si, 256 << si
         for bi in range(n_blocks):
             block = "abcdefgh"[bi]
-            layers += _bottleneck(stage, block, bottom, mid, out, 2 if (bi == 0 and stage > 2) else 1, project=bi == 0)
+            layers += _bottleneck(stage, block, bottom, mid, out, 2 if (bi == 0 and stage > 2) else 1, project=bi == 0,
+                                  stride_on_3x3=stride_on_3x3)
             bottom = "res%d%s" % (stage, block)
     hp = lambda: [_param(1.0, 1.0), _param(2.0, 0)]
     layers += [

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.shf_abi_version() == L.ABI_VERSION == 7                    # a plain host function: safe without a GPU
+    assert lib.shf_abi_version() == L.ABI_VERSION == 8                    # a plain host function: safe without a GPU
     assert lib.shf_last_error() is not None
 
 

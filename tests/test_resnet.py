@@ -187,6 +187,51 @@ def test_strided_1x1_conv_matches_oracle(cin, cout, H, W, s, fmt):
 
 @needs_gpu
 @pytest.mark.skipif(not HAVE_GPU, reason="no CUDA device")
+@pytest.mark.parametrize("cin,cout,H,W,fmt,batch", [(128, 128, 28, 28, 0, 2), (64, 64, 17, 23, 0, 1), (256, 256, 31, 45, 1, 2), (128, 256, 56, 56, 1, 1),
+                                                    (64, 128, 2, 2, 0, 1), (512, 512, 9, 14, 0, 1)])
+def test_conv3x3_stride2_matches_oracle(cin, cout, H, W, fmt, batch):
+    """shf_conv3x3_s2: the 3x3 stride-2 pad-1 convolution on the four parity views of the input (one TMA load per tap and
+    64-channel chunk) against the oracle's strided convolution -- even / odd sizes, both tile widths, both formats."""
+    rng = np.random.RandomState(cin + H + W)
+    x = (rng.randn(batch, cin, H, W) * 20).astype(F32)
+    w = (rng.randn(cout, cin, 3, 3) * np.sqrt(2.0 / (9 * cin))).astype(F32)
+    b = (rng.randn(cout) * 0.05).astype(F32)
+    h = H2.from_nchw(dev(x), fmt)
+    ref = OL.relu(OL.conv(h.to_nchw().cpu().numpy(), w, b, pad=(1, 1), stride=(2, 2)))
+    packed, kexp = (pack_conv_weights_hf8 if fmt else pack_conv_weights)(w)
+    out = H2.empty(batch, ref.shape[2], ref.shape[3], cout, DEV, fmt)
+    L.call("shf_conv3x3_s2", _ptr(h.t), _ptr(dev(packed)), _ptr(dev(b)), _ptr(out.t), batch, H, W, cin, cout, cout, 0,
+           float(2.0 ** -kexp), 1, fmt, fmt, None, _stream())
+    got = out.to_nchw().cpu().numpy()
+    assert got.shape == ref.shape and relerr(got, ref) < (3e-6 if fmt == 0 else 3e-4)
+
+
+@needs_gpu
+@pytest.mark.skipif(not HAVE_GPU, reason="no CUDA device")
+def test_resnet_with_the_stride_on_the_3x3_convolution(tmp_path):
+    """The torchvision / "v1.5" bottleneck (stride on the 3x3 convolution of the stage transition) as a whole net."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_net import BOX_TOL, SCORE_TOL, match_rows
+    hw = (150, 202)
+    proto, model = deploy.write_synthetic_resnet_deployment(str(tmp_path), blocks=(2, 3), input_hw=hw, stride_on_3x3=True)
+    spec = NetSpec(cp.read_net_text(proto))
+    gnet = GpuNet(spec, load_weights(spec, cp.read_net_binary(model)), "cuda:0", fast_min_scale=None)
+    assert sum(1 for k, _, s in gnet.ops if k == "conv" and s["stride"] == 2 and s["k"] == 3) == 1
+    onet = IndepNet(proto, model, engine="torch")
+    data, info = _data(*hw), np.array([[hw[0], hw[1], 1.0]], F32)
+    ref = onet.forward(data=data, im_info=info)
+    boxes, probs, rows = gnet.forward(torch.from_numpy(data).to(DEV), info[0])
+    torch.cuda.synchronize()
+    R = int(rows.item())
+    for nm in ("res3a_branch2b", "res3a", "res3c", "head"):
+        assert relerr(gnet.blob_nchw(nm).cpu().numpy(), onet.blobs[nm]) < 2e-5, nm
+    ws, wb = match_rows(boxes[:R].cpu().numpy()[:, 1:], probs[:R].cpu().numpy()[:, 1], ref["boxes"][:, 1:], ref["cls_prob"][:, 1])
+    print("resnet (stride on the 3x3) rows %d (ref %d): worst score err %.2e, worst box err %.2e px" % (R, len(ref["boxes"]), ws, wb))
+    assert R > 20 and ws < SCORE_TOL and wb < BOX_TOL
+
+
+@needs_gpu
+@pytest.mark.skipif(not HAVE_GPU, reason="no CUDA device")
 @pytest.mark.parametrize("cin,cout,k,H,W,fmt,relu", [(64, 256, 1, 20, 28, 0, 1), (512, 128, 1, 9, 13, 1, 1), (128, 128, 3, 17, 24, 0, 0),
                                                     (256, 64, 1, 16, 16, 1, 1)])
 def test_conv_with_fused_residual_matches_oracle(cin, cout, k, H, W, fmt, relu):
