@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -135,7 +136,7 @@ def pack_conv_first_tc_weights(w_oihw: np.ndarray) -> Tuple[np.ndarray, int]:
 FMT_H2, FMT_HF8 = L.FMT_H2, L.FMT_HF8
 
 # conv1_1 kernel: "pair" = two threads per pixel (conv_first_tc.cu), "single" = one thread per pixel (conv1_tc.cu)
-_CONV1_IMPL = __import__("os").environ.get("SHF_CONV1_IMPL", "single")
+_CONV1_IMPL = os.environ.get("SHF_CONV1_IMPL", "single")
 
 # Range guard thresholds (see include/shf_b200.h, `range_guard`): max |x| of every activation tensor a launch writes.
 F16_MAX = 65504.0          # hi = rn_f16(x) overflows above this in EITHER format: the forward is invalid -> raise
