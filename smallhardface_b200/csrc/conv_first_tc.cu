@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreadsFc, MINB) conv_first_tc_kernel(const F
   using C = Fc<KS, ST>;
   constexpr int kPer = C::kPer, kPH = C::kPH, kPW = C::kPW, kHaloWords = C::kHaloWords, kKSteps = C::kKSteps;
   constexpr int kOffWhi = C::kOffWhi, kOffWlo = C::kOffWlo, kOffStage = C::kOffStage, kOffBar = C::kOffBar;
-  constexpr int kOffBias = C::kOffBias, kOffHalo = C::kOffHalo, kST = ST, kThreads7 = kThreadsFc;
+  constexpr int kOffBias = C::kOffBias, kOffHalo = C::kOffHalo, kST = ST;
   constexpr int kWChunks = C::kWBlocks * 8;               // 16-byte chunks per packed weight row
 
   extern __shared__ uint8_t smem_raw[];
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreadsFc, MINB) conv_first_tc_kernel(const F
   const int m = quad * 32 + lane;                // operand / accumulator row = output pixel (y_local * 8 + x_local)
 
   // weights -> shared memory, 128-byte-swizzled K-major column blocks (16-byte chunk j of row n at j ^ (n & 7))
-  for (int i = threadIdx.x; i < 2 * 64 * kWChunks; i += kThreads7) {
+  for (int i = threadIdx.x; i < 2 * 64 * kWChunks; i += kThreadsFc) {
     const int which = i / (64 * kWChunks), n = (i / kWChunks) % 64, ch = i % kWChunks;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.wpack) + i);
     *reinterpret_cast<uint4*>(smem + (which ? kOffWlo : kOffWhi) + (ch >> 3) * kBBlock + n * 128 + (((ch & 7) ^ (n & 7)) << 4)) = v;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsFc, MINB) conv_first_tc_kernel(const F
   int h_rs[kPer];            // (channel << 16) | (row << 8) | column of this thread's patch positions, -1 = unused slot
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
-    const int idx = (int)threadIdx.x + i * kThreads7;
+    const int idx = (int)threadIdx.x + i * kThreadsFc;
     const int c = idx / (kPH * kPW), rem = idx % (kPH * kPW), r = rem / kPW, s2 = rem % kPW;
     h_rs[i] = idx < kHaloWords ? ((c << 16) | (r << 8) | s2) : -1;
   }
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreadsFc, MINB) conv_first_tc_kernel(const F
       __half hi, lo;
       split_h2(nxt[i], hi, lo);
       if (h_rs[i] >= 0)
-        halo_s[threadIdx.x + i * kThreads7] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+        halo_s[threadIdx.x + i * kThreadsFc] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
     }
     __syncthreads();
     // ---- this pixel's operand row: this thread builds half of the chunks of the hi part (8 taps each) and their twins in
